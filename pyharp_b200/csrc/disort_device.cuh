@@ -1,0 +1,160 @@
+// disort_device.cuh -- per-solve device math of the B200-native DISORT flux path.
+//
+// One CUDA thread owns one independent (wave, column) solve and walks the column
+// top-down.  This is NOT the cdisort algorithm re-typed: the same discrete-ordinate
+// boundary-value problem (c_disort: c_sol_eigen/c_asymmetric_matrix, c_upbeam,
+// c_upisot, c_set_matrix, c_solve0/c_sgbco/c_sgbsl, c_fluxes -- SURVEY.md 8 a6-a15,
+// called from pyharp at src/rtsolver/rt_solver_disort.cpp_:147) is solved with a
+// formulation chosen for registers and FP64 FMA throughput:
+//
+//  * reduced nn x nn (nn = nstr/2) eigenproblem made SYMMETRIC by the stream scaling
+//    u^ = sqrt(mu_i w_i) u  ->  Cholesky + cyclic Jacobi, no Hessenberg/QR, no branches
+//    on data except convergence;
+//  * beam and thermal particular solutions obtained from that eigen-decomposition
+//    (no extra nstr x nstr LU as in c_upbeam / c_upisot);
+//  * the (9nn-2) x (nstr*nlyr) banded LU of c_set_matrix/c_sgbco is replaced by the
+//    mathematically equivalent interaction-principle (adding) sweep on nn x nn layer
+//    reflection/transmission operators: O(nn^2) live state per solve, one forward
+//    (top-down) sweep that stores (nn^2+2nn+1) doubles per level in a coalesced HBM
+//    workspace and one backward sweep that emits the fluxes (c_fluxes).
+//
+// All of it is FP64.  The file is also compiled by g++ for the test-only host
+// simulator (tests/hostsim), hence the B200_HD macros; the product library only
+// ever instantiates it inside __global__ kernels.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define B200_HD __host__ __device__ __forceinline__
+#else
+#define B200_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define B200_RCP(x) __drcp_rn(x)
+#define B200_RSQRT(x) rsqrt(x)
+#else
+#define B200_RCP(x) (1.0 / (x))
+#define B200_RSQRT(x) (1.0 / sqrt(x))
+#endif
+
+namespace b200 {
+
+constexpr int kMaxNN = 16;  // nstr <= 32
+constexpr double kPi = 3.14159265358979323846;
+
+// status words (include/b200disort.h)
+enum : int { ST_OK = 0, ST_BAD_INPUT = 1, ST_EIGEN_FAIL = 2, ST_SINGULAR = 3, ST_UNSUPPORTED = 4, ST_BEAM_ANGLE = 5 };
+
+enum : unsigned { F_USRTAU = 1u, F_USRANG = 2u, F_LAMBER = 4u, F_PLANCK = 8u, F_ONLYFL = 16u, F_INTCOR = 32u, F_OLDINTCOR = 64u };
+
+// Quadrature-dependent tables for azimuth mode 0 (built on the host, constant memory on
+// the device).  Streams i = 0..nn-1 ascending in mu (double-Gauss on (0,1)).
+struct QuadTables {
+  double mu[kMaxNN];    // quadrature cosines
+  double rmu[kMaxNN];   // 1/mu
+  double wt[kMaxNN];    // weights
+  double t[kMaxNN];     // sqrt(mu*w)  (stream scaling)
+  double ehat[kMaxNN];  // sqrt(w/mu)
+  double yhat[2 * kMaxNN][kMaxNN];  // sqrt(w_i/mu_i) * P_l(mu_i), l = 0..nstr-1
+};
+
+struct SolveParams {
+  int nwave, ncol, nlyr, nprop, nstr;
+  unsigned flags;
+  const double* prop;  // (nwave,ncol,nlyr,nprop), layer 0 = surface
+  const double *umu0, *fbeam, *albedo, *btemp, *ttemp, *temis, *fisot;  // (nwave,ncol) or null
+  const double* pkag;        // (nband,ncol,nlyr+1) Planck emission per level, DISORT (top-down) order
+  const int* wave2band;      // (nwave)
+  const double* wave_lower;  // (nwave) or null
+  const double* wave_upper;
+  double* flx;     // (nwave,ncol,nlyr+1,2), level 0 = surface
+  int32_t* status; // (nwave,ncol)
+  double* ws;      // back-sweep workspace: [level][elem][thread]
+  long ws_threads; // number of threads (stride of the fastest workspace axis)
+};
+
+// ---------------------------------------------------------------------------
+// c_planck_func1 (PLKAVG) on the device: identical series / cut-offs / legacy
+// constants as the oracle; parity needs the same series, not a
+// better Planck integral.
+// ---------------------------------------------------------------------------
+B200_HD double plkf(double x) { return x * x * x / (exp(x) - 1.0); }
+
+B200_HD double plkavg(double wnumlo, double wnumhi, double t) {
+  const double a1 = 1.0 / 3.0, a2 = -1.0 / 8.0, a3 = 1.0 / 60.0, a4 = -1.0 / 5040.0,
+               a5 = 1.0 / 272160.0, a6 = -1.0 / 13305600.0;
+  const double c2 = 1.438786, sigma = 5.67032e-8, vcut = 1.5;
+  const double vcp[7] = {10.25, 5.7, 3.9, 2.9, 2.3, 1.9, 0.0};
+  const double vmax = 709.782712893384;  // log(DBL_MAX)
+  const double epsil = 2.220446049250313e-16;
+  const double sigdpi = sigma / kPi;
+  const double conc = 15.0 / (kPi * kPi * kPi * kPi);
+  if (t < 1.0e-4) return 0.0;
+  double v[2] = {c2 * wnumlo / t, c2 * wnumhi / t};
+  if (v[0] > epsil && v[1] < vmax && (wnumhi - wnumlo) / wnumhi < 1.0e-2) {
+    double hh = v[1] - v[0], oldval = 0.0, val = 0.0;
+    double val0 = plkf(v[0]) + plkf(v[1]);
+    for (int n = 1; n <= 10; ++n) {
+      double del = hh / (2 * n);
+      val = val0;
+      for (int k = 1; k <= 2 * n - 1; ++k) val += 2 * (1 + k % 2) * plkf(v[0] + k * del);
+      val = del / 3.0 * val;
+      if (fabs((val - oldval) / val) <= 1.0e-6) break;
+      oldval = val;
+    }
+    return sigdpi * t * t * t * t * conc * val;
+  }
+  double p[2] = {0, 0}, d[2] = {0, 0};
+  int smallv = 0;
+  for (int i = 0; i < 2; ++i) {
+    if (v[i] < vcut) {
+      ++smallv;
+      double vsq = v[i] * v[i];
+      p[i] = conc * vsq * v[i] * (a1 + v[i] * (a2 + v[i] * (a3 + vsq * (a4 + vsq * (a5 + vsq * a6)))));
+    } else {
+      int mmax = 0;
+      do { ++mmax; } while (v[i] < vcp[mmax - 1]);
+      double ex = exp(-v[i]), exm = 1.0, acc = 0.0;
+      for (int m = 1; m <= mmax; ++m) {
+        double mv = m * v[i];
+        exm = ex * exm;
+        acc += exm * (6.0 + mv * (6.0 + mv * (3.0 + mv))) / ((double)m * m * m * m);
+      }
+      d[i] = conc * acc;
+    }
+  }
+  double ans;
+  if (smallv == 2) ans = p[1] - p[0];
+  else if (smallv == 1) ans = 1.0 - p[0] - d[1];
+  else ans = d[0] - d[1];
+  return sigdpi * t * t * t * t * ans;
+}
+
+// packed lower-triangular index (i >= j)
+B200_HD constexpr int sym(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+
+constexpr int kMaxSweeps = 16;
+
+// fully unrolled instantiation (small nn: registers)
+#define B200_UNROLL _Pragma("unroll")
+#define B200_FN(name) name##_u
+#include "disort_solver_body.inc"
+#undef B200_UNROLL
+#undef B200_FN
+// rolled instantiation (large nn: local memory)
+#define B200_UNROLL _Pragma("unroll 1")
+#define B200_FN(name) name##_r
+#include "disort_solver_body.inc"
+#undef B200_UNROLL
+#undef B200_FN
+
+template <int NN, typename QT>
+B200_HD void solve_flux_one(const SolveParams& p, const QT& qt, long s, long tid) {
+  if constexpr (NN <= 4) solve_flux_one_u<NN>(p, qt, s, tid);
+  else solve_flux_one_r<NN>(p, qt, s, tid);
+}
+
+}  // namespace b200

@@ -1,0 +1,40 @@
+// flux_inst.cu -- one instantiation of K1 (the DISORT flux solve kernel) for nn = B200_NN
+// streams per hemisphere.  One thread = one (wave, column) solve; grid-stride over solves.
+#include "flux_inst.cuh"
+
+#ifndef B200_NN
+#error "compile with -DB200_NN=<nstr/2>"
+#endif
+
+namespace b200 {
+namespace {
+
+__constant__ QuadTables c_qt;
+
+__global__ void __launch_bounds__(128) disort_flux_kernel(SolveParams p) {
+  const long nthreads = (long)gridDim.x * blockDim.x;
+  const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long nsolve = (long)p.nwave * p.ncol;
+  for (long s = tid; s < nsolve; s += nthreads) solve_flux_one<B200_NN>(p, c_qt, s, tid);
+}
+
+cudaError_t upload_tables(const QuadTables* qt) { return cudaMemcpyToSymbol(c_qt, qt, sizeof(QuadTables)); }
+
+cudaError_t occupancy(int block, int* blocks_per_sm) {
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, disort_flux_kernel, block, 0);
+}
+
+cudaError_t launch(const SolveParams& p, unsigned grid, int block, cudaStream_t stream) {
+  disort_flux_kernel<<<grid, block, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+const FluxInst kInst = {B200_NN, B200_NN * B200_NN + 2 * B200_NN + 1, upload_tables, occupancy, launch};
+
+}  // namespace
+
+#define B200_CAT2(a, b) a##b
+#define B200_CAT(a, b) B200_CAT2(a, b)
+const FluxInst* B200_CAT(flux_inst_, B200_NN)() { return &kInst; }
+
+}  // namespace b200

@@ -1,0 +1,30 @@
+// flux_inst.cuh -- per-stream-count instantiations of the flux kernel live in their own
+// translation units (flux_inst.cu compiled with -DB200_NN=<nn>) so they build in parallel.
+// Each TU owns its constant-memory quadrature table.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "disort_device.cuh"
+
+namespace b200 {
+
+struct FluxInst {
+  int nn;
+  int nsave;  // doubles stored per level and solve for the back sweep
+  cudaError_t (*upload_tables)(const QuadTables*);
+  cudaError_t (*occupancy)(int block, int* blocks_per_sm);
+  cudaError_t (*launch)(const SolveParams&, unsigned grid, int block, cudaStream_t);
+};
+
+#define B200_DECL_INST(NN) const FluxInst* flux_inst_##NN();
+B200_DECL_INST(1)
+B200_DECL_INST(2)
+B200_DECL_INST(3)
+B200_DECL_INST(4)
+B200_DECL_INST(6)
+B200_DECL_INST(8)
+B200_DECL_INST(12)
+B200_DECL_INST(16)
+#undef B200_DECL_INST
+
+}  // namespace b200
