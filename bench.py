@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- DISORT solves/s on B200 (BASELINE.json metric), one process per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload amars_lw|amars_sw|lbl|gcm]
+  python bench.py --impl reference ...      # the CPU path (oracle restatement of cdisort) on host cores
+
+A "step" is one pass of the hot path over one batch of synthetic atmospheres: the Planck pre-pass
+(when thermal), the DISORT flux-solve kernel over every (g-point, column) of the batch and the
+weighted band integration.  The default workload is the one the metric is quoted on: amars_lw
+shape, nstr = 8, 80 layers, correlated-k g-points x columns, thermal emission.  Columns are sharded
+over ranks (weak scaling: fixed columns per GPU); the band integration is then rank-local and no
+collective is on the data path.
+
+Reported: `value` = solves/s with inputs resident in HBM (CUDA events, max over ranks);
+`e2e` = the same through Disort.forward() with HOST tensors (pinned), H2D and D2H inside the timed
+region; `roofline` = algorithmic FP64 flops (reference-algorithm count W) per launch
+/ measured kernel duration against the measured DFMA peak, with the HBM view beside it;
+`cpu_baseline` = the oracle on the host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "DISORT solves/sec (nstr=8, 80 layers)"
+DEFAULT_COLS = {"amars_lw": 16384, "amars_sw": 1024, "lbl": 8, "gcm": 2048}
+DEFAULT_NWAVE = {"amars_lw": 32, "amars_sw": 500, "lbl": 100000, "gcm": 32}
+DEFAULT_NLYR = {"amars_lw": 80, "amars_sw": 40, "lbl": 40, "gcm": 60}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="amars_lw", choices=sorted(DEFAULT_COLS))
+    ap.add_argument("--ncol", type=int, default=0, help="columns per GPU")
+    ap.add_argument("--nwave", type=int, default=0)
+    ap.add_argument("--nlyr", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="solves in the cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def shape_of(args):
+    name = args.workload
+    return (args.nwave or DEFAULT_NWAVE[name], args.ncol or DEFAULT_COLS[name], args.nlyr or DEFAULT_NLYR[name])
+
+
+def config_of(args, wl, world):
+    nwave, ncol, nlyr, nprop = wl.shape
+    return {"workload": f"{args.workload}-shape synthetic: {nwave} spectral points x {ncol} columns per GPU x "
+                        f"{nlyr} layers, nstr={wl.nstr}, nprop={nprop}, flags={wl.flag_tokens}",
+            "solves_per_step_per_gpu": wl.nsolve, "nstr": wl.nstr, "nlyr": nlyr, "nwave": nwave,
+            "ncol_per_gpu": ncol, "sharding": f"columns x{world}, no data-path collective",
+            "l2": "inputs (%.0f MB) and back-sweep workspace exceed the 126 MB L2; no explicit flush"
+                  % (wl.prop.nbytes / 1e6),
+            "flops_per_solve_W": wl.flops_per_solve(), "bytes_per_solve_Q": wl.bytes_per_solve()}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU leg: the oracle (a restatement of cdisort; the real cdisort is un-vendored)
+# ---------------------------------------------------------------------------------------------
+def cpu_sample(args, wl_name, nsolve_target):
+    from pyharp_b200 import workloads as W
+    nwave, _, nlyr = shape_of(args)
+    nw = min(nwave, 32)
+    ncol = max(1, nsolve_target // nw)
+    return W.make(wl_name, nwave=nw, ncol=ncol, nlyr=nlyr, variant=7)
+
+
+def run_oracle(wl, nthreads):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    t0 = time.perf_counter()
+    _, _, st = O.forward(wl.prop, wl.bc, wl.temf, nstr=wl.nstr, flags=wl.flags, wave_lower=wl.wave_lower,
+                         wave_upper=wl.wave_upper, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    assert not st.any()
+    return dt
+
+
+def cpu_baseline(args):
+    cores = os.cpu_count() or 1
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    O.lib()
+    probe = cpu_sample(args, args.workload, 64 * cores)
+    dt = run_oracle(probe, cores)
+    rate = probe.nsolve / dt
+    n = args.cpu_sample or int(min(max(rate * 10.0, 64 * cores), 4e6))
+    wl = cpu_sample(args, args.workload, n)
+    dt = run_oracle(wl, cores)
+    return {"value": wl.nsolve / dt, "unit": "solves/s", "cores": cores, "kind": "port",
+            "sample": f"{wl.nsolve} solves of the same workload shape ({wl.shape[0]} spectral points x {wl.shape[1]} "
+                      f"columns x {wl.shape[2]} layers) in {dt:.2f} s, OpenMP over solves; oracle/ restatement of "
+                      f"cdisort (cdisort itself is un-vendored in the reference)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    O.lib()
+    probe = cpu_sample(args, args.workload, 64 * cores)
+    rate = probe.nsolve / run_oracle(probe, cores)
+    # bound the whole run to about two minutes of CPU wall time
+    per_step = max(64 * cores, int(rate * min(10.0, 120.0 / max(1, args.steps + args.warmup))))
+    wl = cpu_sample(args, args.workload, per_step)
+    for _ in range(args.warmup):
+        run_oracle(wl, cores)
+    t = 0.0
+    for _ in range(args.steps):
+        t += run_oracle(wl, cores)
+    v = wl.nsolve * args.steps / t
+    nwave, ncol, nlyr = shape_of(args)
+    full = cpu_sample(args, args.workload, 1)  # only for the config text
+    sample = (f"each step = {wl.nsolve} solves ({wl.shape[0]} x {wl.shape[1]} columns x {wl.shape[2]} layers) of the "
+              f"workload, OpenMP over solves on {cores} threads")
+    out = {"metric": METRIC, "value": v, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+           "config": {"workload": f"{args.workload}-shape synthetic: {nwave} spectral points x {ncol} columns per GPU "
+                                  f"x {nlyr} layers, nstr={full.nstr} (CPU arm: bounded sample per step)",
+                      "nstr": full.nstr, "nlyr": nlyr},
+           "cpu_baseline": {"value": v, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": v, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (NVML), running during the timed region
+# ---------------------------------------------------------------------------------------------
+class Clocks:
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._th = None
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            self.N = N
+            self.h = N.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.N = None
+            self.err = repr(e)
+
+    def _loop(self):
+        N = self.N
+        names = {getattr(N, k): k.replace("nvmlClocksThrottleReason", "").replace("nvmlClocksEventReason", "")
+                 for k in dir(N) if k.startswith("nvmlClocksThrottleReason") and k not in
+                 ("nvmlClocksThrottleReasonAll", "nvmlClocksThrottleReasonNone")}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM))
+                r = N.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if bit and (r & bit):
+                        self.reasons.add(nm)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.N:
+            self._th = threading.Thread(target=self._loop, daemon=True)
+            self._th.start()
+
+    def stop(self):
+        if self._th:
+            self._stop.set()
+            self._th.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": getattr(self, "err", "no samples")}
+        idle = {"GpuIdle", "ApplicationsClocksSetting"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(r for r in self.reasons if r not in idle), "samples": len(self.samples)}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from pyharp_b200 import Disort, fp64_peak_tflops, workloads as W, _cabi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    nwave, ncol, nlyr = shape_of(args)
+    wl = W.make(args.workload, nwave=nwave, ncol=ncol, nlyr=nlyr, variant=rank)
+    ds = Disort(wl.options())
+    weights = torch.full((nwave,), 1.0 / nwave, dtype=torch.float64, device=dev)
+
+    # ---- device-resident leg
+    to_dev = lambda a: None if a is None else torch.from_numpy(a).to(dev)
+    d_prop = to_dev(wl.prop)
+    d_bc = {k: to_dev(v) for k, v in wl.bc.items()}
+    d_temf = to_dev(wl.temf)
+    bcs = _cabi.BC()
+    for k, v in d_bc.items():
+        setattr(bcs, k, v.data_ptr())
+    d_flx = torch.empty((nwave, ncol, nlyr + 1, 2), dtype=torch.float64, device=dev)
+    d_status = torch.empty((nwave, ncol), dtype=torch.int32, device=dev)
+    tptr = None if d_temf is None else d_temf.data_ptr()
+
+    def step_device():
+        ds.forward_device_async(d_prop, bcs, tptr, d_flx, d_status)
+        return ds.reduce_band(d_flx, weights)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        bflx = step_device()
+    torch.cuda.synchronize()
+    assert int(d_status.abs().sum()) == 0, "non-zero solve status in the bench workload"
+    assert bool(torch.isfinite(bflx).all())
+    ds.stats()  # reset the kernel-time accumulator
+    launches_per_step = 2 + (1 if wl.thermal else 0)  # planck pre-pass, flux solve, band reduction
+
+    clocks = Clocks(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    clocks.start()
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    st = ds.stats()
+    kernel_ms = st["solve_kernel_ms"] / max(1, st["solves_timed"])
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = wl.nsolve * world * args.steps / (ms_max * 1e-3)
+
+    # ---- end-to-end leg: host (pinned) tensors through the public API
+    e2e = None
+    if not args.no_e2e:
+        h_prop = torch.from_numpy(wl.prop).pin_memory()
+        h_bc = {k: torch.from_numpy(v).pin_memory() for k, v in wl.bc.items()}
+        h_temf = None if wl.temf is None else torch.from_numpy(wl.temf).pin_memory()
+        h2d = h_prop.nbytes + sum(v.nbytes for v in h_bc.values()) + (0 if h_temf is None else h_temf.nbytes)
+        flx = None
+        for _ in range(2):
+            flx = ds.forward(h_prop, h_bc, h_temf)
+        d2h = flx.nbytes + nwave * ncol * 4
+        esteps = max(3, min(args.steps, 10))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            flx = ds.forward(h_prop, h_bc, h_temf)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": wl.nsolve * world * esteps / float(t.item()), "unit": "solves/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": esteps,
+               "api": "pyharp_b200.Disort.forward(host tensors) -> b200disort_solve_host"}
+        ds.stats()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        fp64_peak = fp64_peak_tflops(local)
+        W_, Q_ = wl.flops_per_solve(), wl.bytes_per_solve()
+        ach_tf = W_ * wl.nsolve / (kernel_ms * 1e-3) / 1e12
+        ach_gbs = Q_ * wl.nsolve / (kernel_ms * 1e-3) / 1e9
+        out = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
+               "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": config_of(args, wl, world), "clocks": clk,
+               "gpu_launches": launches_per_step * args.steps,
+               "kernel": {"name": "disort_flux_kernel", "avg_ms": kernel_ms, "share_of_step": kernel_ms / (ms / args.steps),
+                          "workspace_bytes": st["workspace_bytes"]},
+               "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                            "frac": ach_tf / fp64_peak, "traffic": None,
+                            "peak_source": "DFMA-saturating kernel measured in this run (b200disort_fp64_peak); "
+                                           "profiles/microbench/fp64_peak_r01.json has the sweep",
+                            "note": "achieved = reference-algorithm flop count W x solves / kernel time; the adding-"
+                                    "method kernel executes fewer flops than W (see DESIGN.md)"},
+               "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+                                "frac": ach_gbs / hbm_peak, "peak_source": hbm_src},
+               "e2e": e2e}
+        if not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -91,11 +91,13 @@ typedef struct {
   const double *umu0, *fbeam, *albedo, *btemp, *ttemp, *temis, *fisot, *phi0;
 } b200disort_bc;
 
-/* timing / launch statistics of the most recent solve on a handle */
+/* timing / launch statistics of a handle (b200disort_get_stats synchronises, reports, resets) */
 typedef struct {
   int kernel_launches;     /* kernels launched by the last solve call */
-  float solve_kernel_ms;   /* device time of the dominant solve kernel (CUDA events on the handle's stream) */
-  float total_device_ms;   /* all kernels of the call */
+  int solves_timed;        /* solve calls since the previous get_stats */
+  float solve_kernel_ms;   /* summed device time of the dominant solve kernel over those calls
+                              (CUDA events on the handle's stream around each launch) */
+  float total_device_ms;   /* last call: first kernel start to solve kernel end */
   uint64_t workspace_bytes;
 } b200disort_stats;
 

@@ -30,7 +30,7 @@ class BC(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [("kernel_launches", C.c_int), ("solve_kernel_ms", C.c_float),
+    _fields_ = [("kernel_launches", C.c_int), ("solves_timed", C.c_int), ("solve_kernel_ms", C.c_float),
                 ("total_device_ms", C.c_float), ("workspace_bytes", C.c_uint64)]
 
 

@@ -118,7 +118,12 @@ struct b200disort_handle {
   double *h_pin = nullptr, *d_stage = nullptr;
   size_t pin_bytes = 0, stage_bytes = 0;
   int32_t* d_status_own = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  // ring of event pairs around the solve kernel: get_stats sums every solve since the last call
+  static constexpr int kRing = 256;
+  cudaEvent_t ev0 = nullptr, evA[kRing] = {nullptr}, evB[kRing] = {nullptr};
+  int ring_used = 0;
+  double ring_carry_ms = 0.0;  // durations folded in when the ring wrapped
+  int solves_since_stats = 0;
   b200disort_stats stats{};
 };
 
@@ -230,8 +235,10 @@ extern "C" int b200disort_create(const b200disort_config* cfg, b200disort_handle
   CU_TRY(cudaMalloc(&h->d_flag, sizeof(int) * 2));
   CU_TRY(cudaMemset(h->d_flag, 0, sizeof(int) * 2));
   CU_TRY(cudaEventCreate(&h->ev0));
-  CU_TRY(cudaEventCreate(&h->ev1));
-  CU_TRY(cudaEventCreate(&h->ev2));
+  for (int i = 0; i < b200disort_handle::kRing; ++i) {
+    CU_TRY(cudaEventCreate(&h->evA[i]));
+    CU_TRY(cudaEventCreate(&h->evB[i]));
+  }
   *out = h;
   return B200DISORT_OK;
 }
@@ -245,8 +252,10 @@ extern "C" void b200disort_destroy(b200disort_handle* h) {
   cudaFree(h->d_stage); cudaFree(h->d_status_own);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   if (h->ev0) cudaEventDestroy(h->ev0);
-  if (h->ev1) cudaEventDestroy(h->ev1);
-  if (h->ev2) cudaEventDestroy(h->ev2);
+  for (int i = 0; i < b200disort_handle::kRing; ++i) {
+    if (h->evA[i]) cudaEventDestroy(h->evA[i]);
+    if (h->evB[i]) cudaEventDestroy(h->evB[i]);
+  }
   delete h;
 }
 
@@ -269,9 +278,20 @@ static int launch_flux(b200disort_handle* h, SolveParams& p) {
   }
   p.ws = h->d_ws;
   p.ws_threads = nthreads;
-  CU_TRY(cudaEventRecord(h->ev1, h->stream));
+  if (h->ring_used == b200disort_handle::kRing) {  // fold the ring (blocks until those solves finished)
+    CU_TRY(cudaEventSynchronize(h->evB[h->ring_used - 1]));
+    for (int i = 0; i < h->ring_used; ++i) {
+      float ms = 0.f;
+      CU_TRY(cudaEventElapsedTime(&ms, h->evA[i], h->evB[i]));
+      h->ring_carry_ms += ms;
+    }
+    h->ring_used = 0;
+  }
+  CU_TRY(cudaEventRecord(h->evA[h->ring_used], h->stream));
   CU_TRY(inst->launch(p, (unsigned)grid, block, h->stream));
-  CU_TRY(cudaEventRecord(h->ev2, h->stream));
+  CU_TRY(cudaEventRecord(h->evB[h->ring_used], h->stream));
+  h->ring_used += 1;
+  h->solves_since_stats += 1;
   h->stats.kernel_launches += 1;
   h->stats.workspace_bytes = h->ws_bytes;
   return B200DISORT_OK;
@@ -290,7 +310,7 @@ extern "C" int b200disort_solve(b200disort_handle* h, const double* prop, int np
     return B200DISORT_ERR_UNSUPPORTED;  // intensity / user-level path: see b200disort_intensity.cu (next)
   }
   CU_TRY(cudaSetDevice(c.device));
-  h->stats = b200disort_stats{};
+  h->stats.kernel_launches = 0;
   CU_TRY(cudaEventRecord(h->ev0, h->stream));
 
   SolveParams p{};
@@ -331,13 +351,24 @@ extern "C" int b200disort_solve(b200disort_handle* h, const double* prop, int np
 extern "C" int b200disort_get_stats(b200disort_handle* h, b200disort_stats* out) {
   if (!h || !out) return B200DISORT_ERR_INVALID;
   CU_TRY(cudaSetDevice(h->cfg.device));
-  CU_TRY(cudaEventSynchronize(h->ev2));
-  float ms = 0.f, tot = 0.f;
-  CU_TRY(cudaEventElapsedTime(&ms, h->ev1, h->ev2));
-  CU_TRY(cudaEventElapsedTime(&tot, h->ev0, h->ev2));
-  h->stats.solve_kernel_ms = ms;
+  double sum = h->ring_carry_ms;
+  float tot = 0.f;
+  if (h->ring_used > 0) {
+    CU_TRY(cudaEventSynchronize(h->evB[h->ring_used - 1]));
+    for (int i = 0; i < h->ring_used; ++i) {
+      float ms = 0.f;
+      CU_TRY(cudaEventElapsedTime(&ms, h->evA[i], h->evB[i]));
+      sum += ms;
+    }
+    CU_TRY(cudaEventElapsedTime(&tot, h->ev0, h->evB[h->ring_used - 1]));
+  }
+  h->stats.solve_kernel_ms = (float)sum;
+  h->stats.solves_timed = h->solves_since_stats;
   h->stats.total_device_ms = tot;
   *out = h->stats;
+  h->ring_used = 0;
+  h->ring_carry_ms = 0.0;
+  h->solves_since_stats = 0;
   return B200DISORT_OK;
 }
 

@@ -298,7 +298,7 @@ class Disort:
         rc = self._lib.b200disort_get_stats(self._h, C.byref(st))
         if rc != _cabi.OK:
             raise RuntimeError(_cabi.strerror(rc))
-        return {"kernel_launches": st.kernel_launches, "solve_kernel_ms": st.solve_kernel_ms,
+        return {"kernel_launches": st.kernel_launches, "solves_timed": st.solves_timed, "solve_kernel_ms": st.solve_kernel_ms,
                 "total_device_ms": st.total_device_ms, "workspace_bytes": st.workspace_bytes}
 
     def reduce_band(self, flx, weights):

@@ -1,0 +1,73 @@
+"""The C-ABI library loads and exports every symbol include/b200disort.h declares; without a GPU
+every computing entry point fails loudly (there is no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from pyharp_b200 import _cabi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "b200disort.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200disort_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    lib = _cabi.lib()
+    names = declared_functions()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/b200disort.h but not exported"
+    assert sorted(_cabi.EXPORTS) == names
+
+
+def test_flag_values_match_header():
+    src = open(os.path.join(ROOT, "include", "b200disort.h")).read()
+    for name in ("USRTAU", "USRANG", "LAMBER", "PLANCK", "ONLYFL", "INTENSITY_CORRECTION",
+                 "OLD_INTENSITY_CORRECTION", "QUIET"):
+        m = re.search(rf"#define B200DISORT_{name} (\d+)u", src)
+        assert m and int(m.group(1)) == getattr(_cabi, name)
+
+
+def test_struct_layouts():
+    assert C.sizeof(_cabi.BC) == 8 * C.sizeof(C.c_void_p)
+    assert _cabi.Config.device.offset > _cabi.Config.wave_upper.offset
+    assert _cabi.lib().b200disort_version().startswith(b"b200disort")
+    assert b"no CPU fallback" in _cabi.lib().b200disort_strerror(_cabi.ERR_CUDA)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the no-device error path cannot be exercised")
+    cfg = _cabi.Config()
+    cfg.nwave = cfg.ncol = cfg.nlyr = 1
+    cfg.nstr = cfg.nmom = 4
+    cfg.flags = _cabi.LAMBER | _cabi.ONLYFL
+    h = C.c_void_p()
+    assert _cabi.lib().b200disort_create(C.byref(cfg), C.byref(h)) == _cabi.ERR_CUDA
+    assert not h.value
+    v = C.c_double()
+    assert _cabi.lib().b200disort_fp64_peak(0, C.byref(v)) == _cabi.ERR_CUDA
+    from pyharp_b200 import Disort, DisortOptions
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Disort(DisortOptions().flags("lamber,onlyfl"))
+
+
+def test_create_rejects_bad_config():
+    cfg = _cabi.Config()
+    h = C.c_void_p()
+    lib = _cabi.lib()
+    assert lib.b200disort_create(None, C.byref(h)) == _cabi.ERR_INVALID
+    cfg.nwave = cfg.ncol = cfg.nlyr = 1
+    cfg.nstr, cfg.nmom, cfg.flags = 5, 8, _cabi.LAMBER | _cabi.ONLYFL   # odd stream count
+    assert lib.b200disort_create(C.byref(cfg), C.byref(h)) == _cabi.ERR_INVALID
+    cfg.nstr, cfg.nmom = 8, 4                                           # nmom < nstr
+    assert lib.b200disort_create(C.byref(cfg), C.byref(h)) == _cabi.ERR_INVALID
+    cfg.nstr, cfg.nmom, cfg.flags = 8, 8, _cabi.ONLYFL                  # non-Lambertian surface
+    assert lib.b200disort_create(C.byref(cfg), C.byref(h)) == _cabi.ERR_UNSUPPORTED
