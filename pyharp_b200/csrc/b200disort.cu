@@ -61,11 +61,26 @@ __global__ void planck_prepass_kernel(int nband, int ncol, int nlyr, const doubl
 // ---------------------------------------------------------------------------
 // K5: weighted band reduction bflx(ncol,nlev,2) = sum_n w_n flx(n,ncol,nlev,2)
 // ---------------------------------------------------------------------------
+// Deterministic two-stage form: blockIdx.y owns a contiguous slice of spectral points and writes
+// a partial sum (or the result when gridDim.y == 1); reduce_parts_kernel adds the partials in
+// slice order.  Threads run along `inner` (coalesced); the slices give enough CTAs when nwave is
+// large and ncol small (line-by-line: 1e5 spectral points x 1 column).
 __global__ void reduce_band_kernel(int nwave, long inner, const double* __restrict__ flx,
                                    const double* __restrict__ w, double* __restrict__ out) {
+  const int per = (nwave + gridDim.y - 1) / gridDim.y;
+  const int n0 = blockIdx.y * per, n1 = min(nwave, n0 + per);
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < inner; i += (long)gridDim.x * blockDim.x) {
     double acc = 0.0;
-    for (int n = 0; n < nwave; ++n) acc = fma(w[n], flx[(long)n * inner + i], acc);
+    for (int n = n0; n < n1; ++n) acc = fma(w[n], flx[(long)n * inner + i], acc);
+    out[(long)blockIdx.y * inner + i] = acc;
+  }
+}
+
+__global__ void reduce_parts_kernel(int parts, long inner, const double* __restrict__ part,
+                                    double* __restrict__ out) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < inner; i += (long)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int k = 0; k < parts; ++k) acc += part[(long)k * inner + i];
     out[i] = acc;
   }
 }
@@ -104,6 +119,7 @@ struct b200disort_handle {
   const b200::FluxInst* inst = nullptr;
   cudaStream_t stream = nullptr;
   int sm_count = 0;
+  int occ = 0;  // resident CTAs per SM of the flux kernel
   std::vector<double> user_tau, user_mu, user_phi, wave_lower, wave_upper;
   // device-side constants
   double *d_wlo = nullptr, *d_whi = nullptr, *d_blo = nullptr, *d_bhi = nullptr;
@@ -114,10 +130,27 @@ struct b200disort_handle {
   double* d_ws = nullptr;
   size_t ws_bytes = 0;
   int* d_flag = nullptr;  // [0] planck bad-T flag, [1] bad status counter
-  // staging for the host-pointer entry point
-  double *h_pin = nullptr, *d_stage = nullptr;
-  size_t pin_bytes = 0, stage_bytes = 0;
-  int32_t* d_status_own = nullptr;
+  double* d_part = nullptr;  // partial sums of reduce_band
+  size_t part_bytes = 0;
+  // host-pointer entry point: the batch is cut into chunks of solves that flow through kSlots
+  // independent (stream, device buffers, pinned staging) slots, so the H2D copy of chunk c+1, the
+  // solve of chunk c and the D2H copy of chunk c-1 run concurrently (copy engines + SMs).
+  static constexpr int kSlots = 3;
+  struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    double* d_buf = nullptr;   // [inputs | flx | status]
+    size_t d_bytes = 0;
+    double* h_buf = nullptr;   // pinned staging, same layout; used only for pageable user memory
+    size_t h_bytes = 0;
+    double* d_ws = nullptr;
+    size_t ws_bytes = 0;
+    // pending copy-out of a finished chunk (pageable destination)
+    long pend_s0 = -1, pend_n = 0;
+  } slots[kSlots];
+  double* d_temf = nullptr;
+  size_t temf_bytes = 0;
+  cudaEvent_t ev_pre = nullptr;
   // ring of event pairs around the solve kernel: get_stats sums every solve since the last call
   static constexpr int kRing = 256;
   cudaEvent_t ev0 = nullptr, evA[kRing] = {nullptr}, evB[kRing] = {nullptr};
@@ -249,8 +282,14 @@ extern "C" void b200disort_destroy(b200disort_handle* h) {
   cudaStreamSynchronize(h->stream);
   cudaFree(h->d_wlo); cudaFree(h->d_whi); cudaFree(h->d_blo); cudaFree(h->d_bhi);
   cudaFree(h->d_w2b); cudaFree(h->d_pkag); cudaFree(h->d_ws); cudaFree(h->d_flag);
-  cudaFree(h->d_stage); cudaFree(h->d_status_own);
-  if (h->h_pin) cudaFreeHost(h->h_pin);
+  cudaFree(h->d_part); cudaFree(h->d_temf);
+  for (auto& sl : h->slots) {
+    if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
+    if (sl.done) cudaEventDestroy(sl.done);
+    cudaFree(sl.d_buf); cudaFree(sl.d_ws);
+    if (sl.h_buf) cudaFreeHost(sl.h_buf);
+  }
+  if (h->ev_pre) cudaEventDestroy(h->ev_pre);
   if (h->ev0) cudaEventDestroy(h->ev0);
   for (int i = 0; i < b200disort_handle::kRing; ++i) {
     if (h->evA[i]) cudaEventDestroy(h->evA[i]);
@@ -259,41 +298,72 @@ extern "C" void b200disort_destroy(b200disort_handle* h) {
   delete h;
 }
 
-static int launch_flux(b200disort_handle* h, SolveParams& p) {
+// grow-only device buffer
+static int ensure_dev(double** ptr, size_t* have, size_t need) {
+  if (need <= *have) return B200DISORT_OK;
+  if (*ptr) CU_TRY(cudaFree(*ptr));
+  *ptr = nullptr;
+  *have = 0;
+  CU_TRY(cudaMalloc(ptr, need));
+  *have = need;
+  return B200DISORT_OK;
+}
+
+// Launch the flux kernel for p.nlocal solves on `stream` with the given back-sweep workspace.
+// timed = record the launch in the handle's event ring (handle stream only).
+static int launch_flux(b200disort_handle* h, SolveParams& p, cudaStream_t stream, double** ws, size_t* ws_bytes,
+                       bool timed) {
   const FluxInst* inst = h->inst;
   const int block = 128;
-  int occ = 0;
-  CU_TRY(inst->occupancy(block, &occ));
-  if (occ < 1) occ = 1;
-  const long nsolve = (long)p.nwave * p.ncol;
-  long grid = std::min<long>((nsolve + block - 1) / block, (long)h->sm_count * occ);
+  if (h->occ == 0) {
+    int occ = 0;
+    CU_TRY(inst->occupancy(block, &occ));
+    h->occ = occ < 1 ? 1 : occ;
+  }
+  long grid = std::min<long>((p.nlocal + block - 1) / block, (long)h->sm_count * h->occ);
   const long nthreads = grid * block;
   const size_t need = (size_t)p.nlyr * inst->nsave * nthreads * sizeof(double);
-  if (need > h->ws_bytes) {
-    if (h->d_ws) CU_TRY(cudaFree(h->d_ws));
-    h->d_ws = nullptr;
-    h->ws_bytes = 0;
-    CU_TRY(cudaMalloc(&h->d_ws, need));
-    h->ws_bytes = need;
-  }
-  p.ws = h->d_ws;
+  int rc = ensure_dev(ws, ws_bytes, need);
+  if (rc != B200DISORT_OK) return rc;
+  p.ws = *ws;
   p.ws_threads = nthreads;
-  if (h->ring_used == b200disort_handle::kRing) {  // fold the ring (blocks until those solves finished)
-    CU_TRY(cudaEventSynchronize(h->evB[h->ring_used - 1]));
-    for (int i = 0; i < h->ring_used; ++i) {
-      float ms = 0.f;
-      CU_TRY(cudaEventElapsedTime(&ms, h->evA[i], h->evB[i]));
-      h->ring_carry_ms += ms;
+  if (timed) {
+    if (h->ring_used == b200disort_handle::kRing) {  // fold the ring (blocks until those solves finished)
+      CU_TRY(cudaEventSynchronize(h->evB[h->ring_used - 1]));
+      for (int i = 0; i < h->ring_used; ++i) {
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, h->evA[i], h->evB[i]));
+        h->ring_carry_ms += ms;
+      }
+      h->ring_used = 0;
     }
-    h->ring_used = 0;
+    CU_TRY(cudaEventRecord(h->evA[h->ring_used], stream));
   }
-  CU_TRY(cudaEventRecord(h->evA[h->ring_used], h->stream));
-  CU_TRY(inst->launch(p, (unsigned)grid, block, h->stream));
-  CU_TRY(cudaEventRecord(h->evB[h->ring_used], h->stream));
-  h->ring_used += 1;
-  h->solves_since_stats += 1;
+  CU_TRY(inst->launch(p, (unsigned)grid, block, stream));
+  if (timed) {
+    CU_TRY(cudaEventRecord(h->evB[h->ring_used], stream));
+    h->ring_used += 1;
+    h->solves_since_stats += 1;
+  }
   h->stats.kernel_launches += 1;
-  h->stats.workspace_bytes = h->ws_bytes;
+  h->stats.workspace_bytes = *ws_bytes;
+  return B200DISORT_OK;
+}
+
+// Planck pre-pass on `stream`: temf (device) -> h->d_pkag
+static int launch_planck(b200disort_handle* h, const double* temf, cudaStream_t stream) {
+  const b200disort_config& c = h->cfg;
+  const size_t elems = (size_t)h->nband * c.ncol * (c.nlyr + 1);
+  size_t have = h->pkag_elems * sizeof(double);
+  int rc = ensure_dev(&h->d_pkag, &have, elems * sizeof(double));
+  h->pkag_elems = have / sizeof(double);
+  if (rc != B200DISORT_OK) return rc;
+  const int block = 256;
+  const long grid = std::min<long>((long)((elems + block - 1) / block), (long)h->sm_count * 8);
+  planck_prepass_kernel<<<(unsigned)grid, block, 0, stream>>>(h->nband, c.ncol, c.nlyr, h->d_blo, h->d_bhi, temf,
+                                                             h->d_pkag, h->d_flag);
+  CU_TRY(cudaGetLastError());
+  h->stats.kernel_launches += 1;
   return B200DISORT_OK;
 }
 
@@ -327,25 +397,14 @@ extern "C" int b200disort_solve(b200disort_handle* h, const double* prop, int np
   p.wave_upper = h->d_whi;
   p.wave2band = h->d_w2b;
 
+  p.s0 = 0;
+  p.nlocal = (long)c.nwave * c.ncol;
   if (planck) {
-    const size_t elems = (size_t)h->nband * c.ncol * (c.nlyr + 1);
-    if (elems > h->pkag_elems) {
-      if (h->d_pkag) CU_TRY(cudaFree(h->d_pkag));
-      h->d_pkag = nullptr;
-      h->pkag_elems = 0;
-      CU_TRY(cudaMalloc(&h->d_pkag, elems * sizeof(double)));
-      h->pkag_elems = elems;
-    }
-    const int block = 256;
-    const long grid = std::min<long>((long)((elems + block - 1) / block), (long)h->sm_count * 8);
-    planck_prepass_kernel<<<(unsigned)grid, block, 0, h->stream>>>(h->nband, c.ncol, c.nlyr, h->d_blo, h->d_bhi,
-                                                                   temf, h->d_pkag, h->d_flag);
-    CU_TRY(cudaGetLastError());
-    h->stats.kernel_launches += 1;
+    int rc = launch_planck(h, temf, h->stream);
+    if (rc != B200DISORT_OK) return rc;
     p.pkag = h->d_pkag;
   }
-
-  return launch_flux(h, p);
+  return launch_flux(h, p, h->stream, &h->d_ws, &h->ws_bytes, true);
 }
 
 extern "C" int b200disort_get_stats(b200disort_handle* h, b200disort_stats* out) {
@@ -390,66 +449,184 @@ extern "C" int b200disort_check_status(b200disort_handle* h, const int32_t* stat
   return flags[1] ? B200DISORT_ERR_SOLVE : B200DISORT_OK;
 }
 
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
 extern "C" int b200disort_solve_host(b200disort_handle* h, const double* prop, int nprop,
                                      const b200disort_bc* bc, const double* temf, double* flx,
                                      double* uu, int32_t* status) {
   if (!h || !prop || !flx || nprop < 1) return B200DISORT_ERR_INVALID;
   const b200disort_config& c = h->cfg;
+  const bool planck = c.flags & B200DISORT_PLANCK;
+  const bool onlyfl = c.flags & B200DISORT_ONLYFL;
+  if (planck && !temf) return B200DISORT_ERR_INVALID;
+  if (!onlyfl || (c.flags & B200DISORT_USRTAU)) {
+    (void)uu;
+    return B200DISORT_ERR_UNSUPPORTED;
+  }
   CU_TRY(cudaSetDevice(c.device));
-  const size_t nsolve = (size_t)c.nwave * c.ncol;
-  const size_t n_prop = nsolve * c.nlyr * nprop;
-  const size_t n_temf = temf ? (size_t)c.ncol * (c.nlyr + 1) : 0;
-  const double* bcs[8] = {nullptr};
+  h->stats.kernel_launches = 0;
+  using Slot = b200disort_handle::Slot;
+  const long nsolve = (long)c.nwave * c.ncol;
+  const int nlev = nlev_out(c);
+  const double* bcs[7] = {nullptr};
   if (bc) {
     bcs[0] = bc->umu0; bcs[1] = bc->fbeam; bcs[2] = bc->albedo; bcs[3] = bc->btemp;
-    bcs[4] = bc->ttemp; bcs[5] = bc->temis; bcs[6] = bc->fisot; bcs[7] = bc->phi0;
+    bcs[4] = bc->ttemp; bcs[5] = bc->temis; bcs[6] = bc->fisot;
   }
-  size_t n_bc = 0;
-  for (int i = 0; i < 8; ++i) if (bcs[i]) n_bc += nsolve;
-  const size_t n_flx = nsolve * nlev_out(c) * 2;
-  const size_t n_in = n_prop + n_temf + n_bc;
-  const size_t n_status = (nsolve * sizeof(int32_t) + 7) / 8;
-  const size_t total = n_in + n_flx + n_status;
-  if (total * sizeof(double) > h->stage_bytes) {
-    if (h->d_stage) CU_TRY(cudaFree(h->d_stage));
-    if (h->h_pin) CU_TRY(cudaFreeHost(h->h_pin));
-    h->d_stage = nullptr; h->h_pin = nullptr; h->stage_bytes = 0;
-    CU_TRY(cudaMalloc(&h->d_stage, total * sizeof(double)));
-    CU_TRY(cudaMallocHost(&h->h_pin, total * sizeof(double)));
-    h->stage_bytes = total * sizeof(double);
+  int n_bc = 0;
+  for (int i = 0; i < 7; ++i) n_bc += bcs[i] ? 1 : 0;
+
+  // chunk = one resident wave of the flux kernel (every CTA slot of the GPU busy once), so the
+  // kernels of successive chunks run back to back while the copy engines move the neighbours
+  if (h->occ == 0) {
+    int occ = 0;
+    CU_TRY(h->inst->occupancy(128, &occ));
+    h->occ = occ < 1 ? 1 : occ;
   }
-  // pack inputs into the pinned block, one H2D copy
-  double* hp = h->h_pin;
-  size_t off = 0;
-  std::memcpy(hp + off, prop, n_prop * sizeof(double));
-  const double* d_prop = h->d_stage + off;
-  off += n_prop;
-  const double* d_temf = nullptr;
-  if (temf) {
-    std::memcpy(hp + off, temf, n_temf * sizeof(double));
-    d_temf = h->d_stage + off;
-    off += n_temf;
-  }
-  const double* d_bcs[8] = {nullptr};
-  for (int i = 0; i < 8; ++i)
-    if (bcs[i]) {
-      std::memcpy(hp + off, bcs[i], nsolve * sizeof(double));
-      d_bcs[i] = h->d_stage + off;
-      off += nsolve;
+  const long wave = (long)h->sm_count * h->occ * 128;
+  const long chunk = std::min(nsolve, wave);
+  const long nchunk = (nsolve + chunk - 1) / chunk;
+  const size_t in_per = (size_t)c.nlyr * nprop + n_bc;  // doubles per solve
+  const size_t out_per = (size_t)nlev * 2;
+  const size_t st_doubles = ((size_t)chunk * sizeof(int32_t) + 7) / 8;
+  const size_t slot_doubles = (size_t)chunk * (in_per + out_per) + st_doubles;
+
+  bool pinned_in = is_pinned(prop), pinned_out = is_pinned(flx) && (!status || is_pinned(status));
+  for (int i = 0; i < 7; ++i)
+    if (bcs[i] && !is_pinned(bcs[i])) pinned_in = false;
+  const bool stage = !(pinned_in && pinned_out);
+
+  if (!h->ev_pre) CU_TRY(cudaEventCreateWithFlags(&h->ev_pre, cudaEventDisableTiming));
+  const int nslot = (int)std::min<long>(b200disort_handle::kSlots, nchunk);
+  for (int k = 0; k < nslot; ++k) {
+    Slot& sl = h->slots[k];
+    if (!sl.stream) CU_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    if (!sl.done) CU_TRY(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    int rc = ensure_dev(&sl.d_buf, &sl.d_bytes, slot_doubles * sizeof(double));
+    if (rc != B200DISORT_OK) return rc;
+    if (stage && slot_doubles * sizeof(double) > sl.h_bytes) {
+      if (sl.h_buf) CU_TRY(cudaFreeHost(sl.h_buf));
+      sl.h_buf = nullptr;
+      sl.h_bytes = 0;
+      CU_TRY(cudaMallocHost(&sl.h_buf, slot_doubles * sizeof(double)));
+      sl.h_bytes = slot_doubles * sizeof(double);
     }
-  CU_TRY(cudaMemcpyAsync(h->d_stage, hp, n_in * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  double* d_flx = h->d_stage + n_in;
-  int32_t* d_status = reinterpret_cast<int32_t*>(h->d_stage + n_in + n_flx);
-  b200disort_bc dbc{d_bcs[0], d_bcs[1], d_bcs[2], d_bcs[3], d_bcs[4], d_bcs[5], d_bcs[6], d_bcs[7]};
-  int rc = b200disort_solve(h, d_prop, nprop, &dbc, d_temf, d_flx, nullptr, d_status);
-  if (rc != B200DISORT_OK) return rc;
-  (void)uu;
-  CU_TRY(cudaMemcpyAsync(hp + n_in, d_flx, (n_flx + n_status) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  int nbad = 0;
-  rc = b200disort_check_status(h, d_status, &nbad);  // synchronises the stream
-  std::memcpy(flx, hp + n_in, n_flx * sizeof(double));
-  if (status) std::memcpy(status, hp + n_in + n_flx, nsolve * sizeof(int32_t));
-  return rc;
+    sl.pend_s0 = -1;
+  }
+
+  // per-column Planck table once, on the handle's stream; the slots wait for it
+  if (planck) {
+    const size_t nb = (size_t)c.ncol * (c.nlyr + 1) * sizeof(double);
+    int rc = ensure_dev(&h->d_temf, &h->temf_bytes, nb);
+    if (rc != B200DISORT_OK) return rc;
+    CU_TRY(cudaMemcpyAsync(h->d_temf, temf, nb, cudaMemcpyHostToDevice, h->stream));
+    rc = launch_planck(h, h->d_temf, h->stream);
+    if (rc != B200DISORT_OK) return rc;
+  }
+  CU_TRY(cudaEventRecord(h->ev_pre, h->stream));
+
+  int32_t* st_out = status;
+  std::vector<int32_t> st_tmp;
+  if (!st_out) {
+    st_tmp.resize((size_t)nsolve);
+    st_out = st_tmp.data();
+  }
+  auto drain = [&](Slot& sl) -> int {  // finish a slot's previous chunk (copy-out when staging)
+    if (sl.pend_s0 < 0) return B200DISORT_OK;
+    CU_TRY(cudaEventSynchronize(sl.done));
+    if (stage) {
+      const double* ho = sl.h_buf + (size_t)chunk * in_per;
+      std::memcpy(flx + (size_t)sl.pend_s0 * out_per, ho, (size_t)sl.pend_n * out_per * sizeof(double));
+      std::memcpy(st_out + sl.pend_s0, ho + (size_t)chunk * out_per, (size_t)sl.pend_n * sizeof(int32_t));
+    }
+    sl.pend_s0 = -1;
+    return B200DISORT_OK;
+  };
+
+  for (long ck = 0; ck < nchunk; ++ck) {
+    Slot& sl = h->slots[ck % nslot];
+    int rc = drain(sl);
+    if (rc != B200DISORT_OK) return rc;
+    const long s0 = ck * chunk, n = std::min(chunk, nsolve - s0);
+    double* d_in = sl.d_buf;
+    double* d_flx = sl.d_buf + (size_t)chunk * in_per;
+    int32_t* d_st = reinterpret_cast<int32_t*>(d_flx + (size_t)chunk * out_per);
+    // inputs: [prop chunk | bc_0 chunk | bc_1 chunk ...]
+    const size_t np = (size_t)n * c.nlyr * nprop;
+    if (stage) {
+      std::memcpy(sl.h_buf, prop + (size_t)s0 * c.nlyr * nprop, np * sizeof(double));
+      size_t off = (size_t)chunk * c.nlyr * nprop;
+      for (int i = 0; i < 7; ++i)
+        if (bcs[i]) {
+          std::memcpy(sl.h_buf + off, bcs[i] + s0, (size_t)n * sizeof(double));
+          off += chunk;
+        }
+      CU_TRY(cudaMemcpyAsync(d_in, sl.h_buf, (size_t)chunk * in_per * sizeof(double), cudaMemcpyHostToDevice, sl.stream));
+    } else {
+      CU_TRY(cudaMemcpyAsync(d_in, prop + (size_t)s0 * c.nlyr * nprop, np * sizeof(double), cudaMemcpyHostToDevice, sl.stream));
+      size_t off = (size_t)chunk * c.nlyr * nprop;
+      for (int i = 0; i < 7; ++i)
+        if (bcs[i]) {
+          CU_TRY(cudaMemcpyAsync(d_in + off, bcs[i] + s0, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, sl.stream));
+          off += chunk;
+        }
+    }
+    SolveParams p{};
+    p.nwave = c.nwave; p.ncol = c.ncol; p.nlyr = c.nlyr; p.nprop = nprop; p.nstr = c.nstr;
+    p.flags = c.flags;
+    p.prop = d_in;
+    {
+      const double** dst[7] = {&p.umu0, &p.fbeam, &p.albedo, &p.btemp, &p.ttemp, &p.temis, &p.fisot};
+      size_t off = (size_t)chunk * c.nlyr * nprop;
+      for (int i = 0; i < 7; ++i)
+        if (bcs[i]) {
+          *dst[i] = d_in + off;
+          off += chunk;
+        }
+    }
+    p.flx = d_flx;
+    p.status = d_st;
+    p.wave_lower = h->d_wlo; p.wave_upper = h->d_whi; p.wave2band = h->d_w2b;
+    p.pkag = h->d_pkag;
+    p.s0 = s0;
+    p.nlocal = n;
+    if (ck < nslot) CU_TRY(cudaStreamWaitEvent(sl.stream, h->ev_pre, 0));
+    rc = launch_flux(h, p, sl.stream, &sl.d_ws, &sl.ws_bytes, false);
+    if (rc != B200DISORT_OK) return rc;
+    if (stage) {
+      CU_TRY(cudaMemcpyAsync(sl.h_buf + (size_t)chunk * in_per, d_flx,
+                             ((size_t)chunk * out_per + st_doubles) * sizeof(double), cudaMemcpyDeviceToHost, sl.stream));
+    } else {
+      CU_TRY(cudaMemcpyAsync(flx + (size_t)s0 * out_per, d_flx, (size_t)n * out_per * sizeof(double),
+                             cudaMemcpyDeviceToHost, sl.stream));
+      if (status)
+        CU_TRY(cudaMemcpyAsync(status + s0, d_st, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream));
+      else
+        CU_TRY(cudaMemcpyAsync(st_out + s0, d_st, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream));
+    }
+    CU_TRY(cudaEventRecord(sl.done, sl.stream));
+    sl.pend_s0 = s0;
+    sl.pend_n = n;
+  }
+  for (int k = 0; k < nslot; ++k) {
+    int rc = drain(h->slots[k]);
+    if (rc != B200DISORT_OK) return rc;
+  }
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  // a negative / NaN level temperature seen by the Planck pre-pass
+  int flag = 0;
+  CU_TRY(cudaMemcpy(&flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag) CU_TRY(cudaMemset(h->d_flag, 0, sizeof(int)));
+  long nbad = 0;
+  for (long i = 0; i < nsolve; ++i) nbad += st_out[i] != 0;
+  return (flag || nbad) ? B200DISORT_ERR_SOLVE : B200DISORT_OK;
 }
 
 extern "C" int b200disort_get_rad(b200disort_handle* h, double* uu) {
@@ -465,7 +642,25 @@ extern "C" int b200disort_reduce_band(b200disort_handle* h, const double* flx, c
   const long inner = (long)c.ncol * nlev_out(c) * 2;
   const int block = 256;
   const long grid = std::min<long>((inner + block - 1) / block, (long)h->sm_count * 8);
-  reduce_band_kernel<<<(unsigned)grid, block, 0, h->stream>>>(c.nwave, inner, flx, weights, bflx);
+  const long want = (long)h->sm_count * 8;  // CTAs that fill the machine
+  int parts = (int)std::min<long>(std::max<long>(1, want / std::max<long>(1, (inner + block - 1) / block)),
+                                  std::max(1, c.nwave / 16));
+  if (parts <= 1) {
+    reduce_band_kernel<<<dim3((unsigned)grid, 1), block, 0, h->stream>>>(c.nwave, inner, flx, weights, bflx);
+    CU_TRY(cudaGetLastError());
+    return B200DISORT_OK;
+  }
+  const size_t need = (size_t)parts * inner * sizeof(double);
+  if (need > h->part_bytes) {
+    if (h->d_part) CU_TRY(cudaFree(h->d_part));
+    h->d_part = nullptr;
+    h->part_bytes = 0;
+    CU_TRY(cudaMalloc(&h->d_part, need));
+    h->part_bytes = need;
+  }
+  reduce_band_kernel<<<dim3((unsigned)grid, (unsigned)parts), block, 0, h->stream>>>(c.nwave, inner, flx, weights, h->d_part);
+  CU_TRY(cudaGetLastError());
+  reduce_parts_kernel<<<(unsigned)grid, block, 0, h->stream>>>(parts, inner, h->d_part, bflx);
   CU_TRY(cudaGetLastError());
   return B200DISORT_OK;
 }

@@ -72,6 +72,8 @@ struct SolveParams {
   const double* wave_upper;
   double* flx;     // (nwave,ncol,nlyr+1,2), level 0 = surface
   int32_t* status; // (nwave,ncol)
+  long s0;         // batch index of this launch's first solve (chunked host path); prop/bc/flx/status are chunk-local
+  long nlocal;     // solves in this launch
   double* ws;      // back-sweep workspace: [level][elem][thread]
   long ws_threads; // number of threads (stride of the fastest workspace axis)
 };

@@ -14,7 +14,7 @@ __constant__ QuadTables c_qt;
 __global__ void __launch_bounds__(128) disort_flux_kernel(SolveParams p) {
   const long nthreads = (long)gridDim.x * blockDim.x;
   const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long nsolve = (long)p.nwave * p.ncol;
+  const long nsolve = p.nlocal;
   for (long s = tid; s < nsolve; s += nthreads) solve_flux_one<B200_NN>(p, c_qt, s, tid);
 }
 

@@ -252,8 +252,11 @@ class Disort:
             temf = temf.to(device=dev, dtype=torch.float64).contiguous()
             keep.append(temf)
             tptr = temf.data_ptr()
-        flx = torch.empty((nw, nc, self.nlev, 2), dtype=torch.float64, device=dev)
-        status = torch.empty((nw, nc), dtype=torch.int32, device=dev)
+        # host results land in pinned memory (torch's caching host allocator) so the chunked D2H
+        # copies of b200disort_solve_host are true async DMA
+        pin = dict(pin_memory=True) if on_host else {}
+        flx = torch.empty((nw, nc, self.nlev, 2), dtype=torch.float64, device=dev, **pin)
+        status = torch.empty((nw, nc), dtype=torch.int32, device=dev, **pin)
         uu = None
         if not onlyfl:
             numu = d.numu if self._flags & _cabi.USRANG else d.nstr

@@ -18,6 +18,8 @@ static void run(SolveParams& p, const QuadTables& qt) {
   std::vector<double> ws((size_t)p.nlyr * NSAVE);
   p.ws = ws.data();
   p.ws_threads = 1;
+  p.s0 = 0;
+  p.nlocal = nsolve;
   for (long s = 0; s < nsolve; ++s) solve_flux_one<NN>(p, qt, s, 0);
 }
 
