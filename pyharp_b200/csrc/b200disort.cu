@@ -17,6 +17,8 @@
 #include "disort_device.cuh"
 #include "flux_inst.cuh"
 #include "host_tables.hpp"
+#include "intensity_device.cuh"
+#include "intensity_launch.hpp"
 
 namespace b200 {
 
@@ -130,6 +132,13 @@ struct b200disort_handle {
   double* d_ws = nullptr;
   size_t ws_bytes = 0;
   int* d_flag = nullptr;  // [0] planck bad-T flag, [1] bad status counter
+  // general (intensity / user-level) path
+  double *d_utau = nullptr, *d_umu = nullptr, *d_phi = nullptr, *d_quad = nullptr;  // d_quad = [cmu | cwt]
+  double* d_uu = nullptr;   // intensities of the last solve (nwave,ncol,nphi,ntau,numu)
+  size_t uu_bytes = 0;
+  double* d_iws = nullptr;  // per-CTA workspaces of the intensity kernel
+  size_t iws_bytes = 0;
+  bool have_uu = false;
   double* d_part = nullptr;  // partial sums of reduce_band
   size_t part_bytes = 0;
   // host-pointer entry point: the batch is cut into chunks of solves that flow through kSlots
@@ -265,6 +274,21 @@ extern "C" int b200disort_create(const b200disort_config* cfg, b200disort_handle
     CU_TRY(cudaMemcpy(h->d_bhi, bhi.data(), sizeof(double) * h->nband, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(h->d_w2b, w2b.data(), sizeof(int) * cfg->nwave, cudaMemcpyHostToDevice));
   }
+  {
+    auto up = [&](const std::vector<double>& v, double** d) -> int {
+      if (v.empty()) return B200DISORT_OK;
+      CU_TRY(cudaMalloc(d, sizeof(double) * v.size()));
+      CU_TRY(cudaMemcpy(*d, v.data(), sizeof(double) * v.size(), cudaMemcpyHostToDevice));
+      return B200DISORT_OK;
+    };
+    std::vector<double> quad(cfg->nstr);
+    for (int i = 0; i < cfg->nstr / 2; ++i) { quad[i] = qt.mu[i]; quad[cfg->nstr / 2 + i] = qt.wt[i]; }
+    int rc = up(h->user_tau, &h->d_utau);
+    if (rc == B200DISORT_OK) rc = up(h->user_mu, &h->d_umu);
+    if (rc == B200DISORT_OK) rc = up(h->user_phi, &h->d_phi);
+    if (rc == B200DISORT_OK) rc = up(quad, &h->d_quad);
+    if (rc != B200DISORT_OK) { delete h; return rc; }
+  }
   CU_TRY(cudaMalloc(&h->d_flag, sizeof(int) * 2));
   CU_TRY(cudaMemset(h->d_flag, 0, sizeof(int) * 2));
   CU_TRY(cudaEventCreate(&h->ev0));
@@ -283,6 +307,7 @@ extern "C" void b200disort_destroy(b200disort_handle* h) {
   cudaFree(h->d_wlo); cudaFree(h->d_whi); cudaFree(h->d_blo); cudaFree(h->d_bhi);
   cudaFree(h->d_w2b); cudaFree(h->d_pkag); cudaFree(h->d_ws); cudaFree(h->d_flag);
   cudaFree(h->d_part); cudaFree(h->d_temf);
+  cudaFree(h->d_utau); cudaFree(h->d_umu); cudaFree(h->d_phi); cudaFree(h->d_quad); cudaFree(h->d_uu); cudaFree(h->d_iws);
   for (auto& sl : h->slots) {
     if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
     if (sl.done) cudaEventDestroy(sl.done);
@@ -367,6 +392,55 @@ static int launch_planck(b200disort_handle* h, const double* temf, cudaStream_t 
   return B200DISORT_OK;
 }
 
+static int ntau_eff(const b200disort_config& c) { return (c.flags & B200DISORT_USRTAU) ? c.ntau : c.nlyr + 1; }
+static int numu_eff(const b200disort_config& c) {
+  return ((c.flags & B200DISORT_USRANG) && !(c.flags & B200DISORT_ONLYFL)) ? c.numu : c.nstr;
+}
+static size_t uu_elems(const b200disort_config& c) {
+  if (c.flags & B200DISORT_ONLYFL) return 0;
+  return (size_t)c.nwave * c.ncol * c.nphi * ntau_eff(c) * numu_eff(c);
+}
+
+// General path (user levels / angles, azimuth series, intensity corrections): K3, one CTA per solve.
+static int solve_general(b200disort_handle* h, const double* prop, int nprop, const b200disort_bc* bc,
+                         const double* temf, double* flx, double* uu, int32_t* status) {
+  const b200disort_config& c = h->cfg;
+  const bool onlyfl = c.flags & B200DISORT_ONLYFL;
+  IntensityParams P{};
+  P.nwave = c.nwave; P.ncol = c.ncol; P.nlyr = c.nlyr; P.nprop = nprop; P.nstr = c.nstr; P.nmom = c.nmom;
+  P.ntau = ntau_eff(c); P.numu = numu_eff(c); P.nphi = onlyfl ? 0 : c.nphi;
+  P.flags = c.flags; P.accur = c.accur;
+  P.prop = prop;
+  if (bc) {
+    P.umu0 = bc->umu0; P.fbeam = bc->fbeam; P.albedo = bc->albedo; P.btemp = bc->btemp;
+    P.ttemp = bc->ttemp; P.temis = bc->temis; P.fisot = bc->fisot; P.phi0 = bc->phi0;
+  }
+  P.temf = temf;
+  P.wave_lower = h->d_wlo; P.wave_upper = h->d_whi;
+  P.utau = h->d_utau; P.umu = h->d_umu; P.phi = h->d_phi;
+  P.cmu = h->d_quad; P.cwt = h->d_quad + c.nstr / 2;
+  P.flx = flx; P.status = status;
+  const size_t nuu = uu_elems(c);
+  if (nuu) {
+    int rc = ensure_dev(&h->d_uu, &h->uu_bytes, nuu * sizeof(double));
+    if (rc != B200DISORT_OK) return rc;
+    P.uu = h->d_uu;
+  }
+  const long nsolve = (long)c.nwave * c.ncol;
+  const long grid = std::min<long>(nsolve, (long)h->sm_count * 4);
+  P.ws_per_cta = intensity_ws_doubles(c.nlyr, c.nstr, P.ntau, P.numu);
+  int rc = ensure_dev(&h->d_iws, &h->iws_bytes, (size_t)grid * P.ws_per_cta * sizeof(double));
+  if (rc != B200DISORT_OK) return rc;
+  P.ws = h->d_iws;
+  P.s0 = 0; P.nlocal = nsolve;
+  CU_TRY(launch_intensity(P, (unsigned)grid, h->stream));
+  h->stats.kernel_launches += 1;
+  h->stats.workspace_bytes = h->iws_bytes;
+  h->have_uu = nuu != 0;
+  if (nuu && uu) CU_TRY(cudaMemcpyAsync(uu, h->d_uu, nuu * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  return B200DISORT_OK;
+}
+
 extern "C" int b200disort_solve(b200disort_handle* h, const double* prop, int nprop,
                                 const b200disort_bc* bc, const double* temf, double* flx,
                                 double* uu, int32_t* status) {
@@ -375,13 +449,10 @@ extern "C" int b200disort_solve(b200disort_handle* h, const double* prop, int np
   const bool planck = c.flags & B200DISORT_PLANCK;
   const bool onlyfl = c.flags & B200DISORT_ONLYFL;
   if (planck && !temf) return B200DISORT_ERR_INVALID;
-  if (!onlyfl || (c.flags & B200DISORT_USRTAU)) {
-    (void)uu;
-    return B200DISORT_ERR_UNSUPPORTED;  // intensity / user-level path: see b200disort_intensity.cu (next)
-  }
   CU_TRY(cudaSetDevice(c.device));
   h->stats.kernel_launches = 0;
   CU_TRY(cudaEventRecord(h->ev0, h->stream));
+  if (!onlyfl || (c.flags & B200DISORT_USRTAU)) return solve_general(h, prop, nprop, bc, temf, flx, uu, status);
 
   SolveParams p{};
   p.nwave = c.nwave; p.ncol = c.ncol; p.nlyr = c.nlyr; p.nprop = nprop; p.nstr = c.nstr;
@@ -466,13 +537,49 @@ extern "C" int b200disort_solve_host(b200disort_handle* h, const double* prop, i
   const bool planck = c.flags & B200DISORT_PLANCK;
   const bool onlyfl = c.flags & B200DISORT_ONLYFL;
   if (planck && !temf) return B200DISORT_ERR_INVALID;
-  if (!onlyfl || (c.flags & B200DISORT_USRTAU)) {
-    (void)uu;
-    return B200DISORT_ERR_UNSUPPORTED;
-  }
   CU_TRY(cudaSetDevice(c.device));
   h->stats.kernel_launches = 0;
   using Slot = b200disort_handle::Slot;
+  if (!onlyfl || (c.flags & B200DISORT_USRTAU)) {
+    // cold path (test_disort-sized batches): stage everything, one launch, copy back
+    const size_t ns = (size_t)c.nwave * c.ncol;
+    const double* src[9] = {bc ? bc->umu0 : nullptr, bc ? bc->fbeam : nullptr, bc ? bc->albedo : nullptr,
+                            bc ? bc->btemp : nullptr, bc ? bc->ttemp : nullptr, bc ? bc->temis : nullptr,
+                            bc ? bc->fisot : nullptr, bc ? bc->phi0 : nullptr, nullptr};
+    const size_t n_prop = ns * c.nlyr * nprop, n_temf = temf ? (size_t)c.ncol * (c.nlyr + 1) : 0;
+    const size_t n_flx = ns * ntau_eff(c) * 2, n_st = (ns * sizeof(int32_t) + 7) / 8;
+    Slot& sl = h->slots[0];
+    int rc = ensure_dev(&sl.d_buf, &sl.d_bytes, (n_prop + n_temf + 8 * ns + n_flx + n_st) * sizeof(double));
+    if (rc != B200DISORT_OK) return rc;
+    double* d = sl.d_buf;
+    CU_TRY(cudaMemcpyAsync(d, prop, n_prop * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    const double* d_prop = d; d += n_prop;
+    const double* d_temf = nullptr;
+    if (temf) {
+      CU_TRY(cudaMemcpyAsync(d, temf, n_temf * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      d_temf = d; d += n_temf;
+    }
+    const double* dbc[8] = {nullptr};
+    for (int i = 0; i < 8; ++i)
+      if (src[i]) {
+        CU_TRY(cudaMemcpyAsync(d, src[i], ns * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        dbc[i] = d; d += ns;
+      }
+    double* d_flx = d; d += n_flx;
+    int32_t* d_st = reinterpret_cast<int32_t*>(d);
+    b200disort_bc dev_bc{dbc[0], dbc[1], dbc[2], dbc[3], dbc[4], dbc[5], dbc[6], dbc[7]};
+    rc = solve_general(h, d_prop, nprop, &dev_bc, d_temf, d_flx, nullptr, d_st);
+    if (rc != B200DISORT_OK) return rc;
+    std::vector<int32_t> st_host(ns);
+    CU_TRY(cudaMemcpyAsync(flx, d_flx, n_flx * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaMemcpyAsync(st_host.data(), d_st, ns * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (uu && uu_elems(c)) CU_TRY(cudaMemcpyAsync(uu, h->d_uu, uu_elems(c) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    long nbad = 0;
+    for (size_t i = 0; i < ns; ++i) nbad += st_host[i] != 0;
+    if (status) std::memcpy(status, st_host.data(), ns * sizeof(int32_t));
+    return nbad ? B200DISORT_ERR_SOLVE : B200DISORT_OK;
+  }
   const long nsolve = (long)c.nwave * c.ncol;
   const int nlev = nlev_out(c);
   const double* bcs[7] = {nullptr};
@@ -630,8 +737,12 @@ extern "C" int b200disort_solve_host(b200disort_handle* h, const double* prop, i
 }
 
 extern "C" int b200disort_get_rad(b200disort_handle* h, double* uu) {
-  (void)h; (void)uu;
-  return B200DISORT_ERR_UNSUPPORTED;
+  if (!h || !uu) return B200DISORT_ERR_INVALID;
+  if (!h->have_uu) return B200DISORT_ERR_INVALID;  // ONLYFL, or no solve yet
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  CU_TRY(cudaMemcpyAsync(uu, h->d_uu, uu_elems(h->cfg) * sizeof(double), cudaMemcpyDefault, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  return B200DISORT_OK;
 }
 
 extern "C" int b200disort_reduce_band(b200disort_handle* h, const double* flx, const double* weights,

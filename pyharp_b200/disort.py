@@ -162,13 +162,13 @@ class Disort:
         d = options.ds()
         flags = options.flag_bits()
         self._flags = flags
-        if options.user_tau():
+        if len(options.user_tau()):
             d.ntau = len(options.user_tau())
             d.utau = list(options.user_tau())
-        if options.user_mu():
+        if len(options.user_mu()):
             d.numu = len(options.user_mu())
             d.umu = list(options.user_mu())
-        if options.user_phi():
+        if len(options.user_phi()):
             d.nphi = len(options.user_phi())
             d.phi = list(options.user_phi())
         self._keep = []

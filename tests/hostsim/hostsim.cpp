@@ -60,3 +60,35 @@ extern "C" int hostsim_flux(int nwave, int ncol, int nlyr, int nstr, int nprop, 
   }
   return 0;
 }
+
+// ---- general (intensity / user-level) path: pyharp_b200/csrc/intensity_device.cuh on the host ----
+#include "../../pyharp_b200/csrc/intensity_device.cuh"
+
+extern "C" int hostsim_intensity(int nwave, int ncol, int nlyr, int nstr, int nmom, int nprop, unsigned flags,
+                                 double accur, int ntau, int numu, int nphi, const double* utau,
+                                 const double* umu, const double* phi, const double* prop, const double* umu0,
+                                 const double* fbeam, const double* albedo, const double* btemp,
+                                 const double* ttemp, const double* temis, const double* fisot,
+                                 const double* phi0, const double* temf, const double* wave_lower,
+                                 const double* wave_upper, double* flx, double* uu, int* status) {
+  QuadTables qt;
+  build_quad_tables(nstr, &qt);
+  IntensityParams P{};
+  P.nwave = nwave; P.ncol = ncol; P.nlyr = nlyr; P.nprop = nprop; P.nstr = nstr; P.nmom = nmom;
+  const bool onlyfl = flags & F_ONLYFL;
+  P.ntau = (flags & F_USRTAU) ? ntau : nlyr + 1;
+  P.numu = ((flags & F_USRANG) && !onlyfl) ? numu : nstr;
+  P.nphi = nphi;
+  P.flags = flags; P.accur = accur;
+  P.prop = prop; P.umu0 = umu0; P.fbeam = fbeam; P.albedo = albedo; P.btemp = btemp; P.ttemp = ttemp;
+  P.temis = temis; P.fisot = fisot; P.phi0 = phi0; P.temf = temf;
+  P.wave_lower = wave_lower; P.wave_upper = wave_upper;
+  P.utau = utau; P.umu = umu; P.phi = phi;
+  P.cmu = qt.mu; P.cwt = qt.wt;
+  P.flx = flx; P.uu = onlyfl ? nullptr : uu; P.status = status;
+  const IntensityWs M = intensity_ws_map(nlyr, nstr, P.ntau, P.numu, 1);
+  std::vector<double> ws((size_t)M.total);
+  P.ws = ws.data(); P.ws_per_cta = M.total; P.s0 = 0; P.nlocal = (long)nwave * ncol;
+  for (long s = 0; s < P.nlocal; ++s) solve_intensity_one(P, s, ws.data(), 0, 1);
+  return 0;
+}
