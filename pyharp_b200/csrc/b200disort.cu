@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -339,11 +340,15 @@ static int ensure_dev(double** ptr, size_t* have, size_t need) {
 static int launch_flux(b200disort_handle* h, SolveParams& p, cudaStream_t stream, double** ws, size_t* ws_bytes,
                        bool timed) {
   const FluxInst* inst = h->inst;
-  const int block = 128;
+  // tuning knobs (profiling only): B200DISORT_BLOCK = threads per CTA (<= 128), B200DISORT_CTAS_PER_SM caps residency
+  static const int env_block = std::getenv("B200DISORT_BLOCK") ? std::atoi(std::getenv("B200DISORT_BLOCK")) : 0;
+  static const int env_ctas = std::getenv("B200DISORT_CTAS_PER_SM") ? std::atoi(std::getenv("B200DISORT_CTAS_PER_SM")) : 0;
+  const int block = (env_block >= 32 && env_block <= 128) ? env_block : 128;
   if (h->occ == 0) {
     int occ = 0;
     CU_TRY(inst->occupancy(block, &occ));
     h->occ = occ < 1 ? 1 : occ;
+    if (env_ctas > 0) h->occ = std::min(h->occ, env_ctas);
   }
   long grid = std::min<long>((p.nlocal + block - 1) / block, (long)h->sm_count * h->occ);
   const long nthreads = grid * block;

@@ -155,7 +155,10 @@ constexpr int kMaxSweeps = 16;
 
 template <int NN, typename QT>
 B200_HD void solve_flux_one(const SolveParams& p, const QT& qt, long s, long tid) {
-  if constexpr (NN <= 4) solve_flux_one_u<NN>(p, qt, s, tid);
+#ifndef B200_UNROLL_MAX_NN
+#define B200_UNROLL_MAX_NN 4
+#endif
+  if constexpr (NN <= B200_UNROLL_MAX_NN) solve_flux_one_u<NN>(p, qt, s, tid);
   else solve_flux_one_r<NN>(p, qt, s, tid);
 }
 
