@@ -38,6 +38,7 @@ EXPORTS = ("b200disort_create", "b200disort_solve", "b200disort_solve_host",
            "b200disort_check_status", "b200disort_get_rad", "b200disort_reduce_band",
            "b200disort_get_stats", "b200disort_fp64_peak", "b200disort_destroy",
            "b200disort_strerror", "b200disort_version")
+OPACITY_EXPORTS = ("b200_interpn", "b200_aerosol_optics", "b200_rfm_optics", "b200_layer2level", "b200_band_optics")
 
 _lib = None
 
@@ -74,6 +75,19 @@ def lib():
     L.b200disort_strerror.restype = C.c_char_p
     L.b200disort_strerror.argtypes = [C.c_int]
     L.b200disort_version.restype = C.c_char_p
+    # include/b200opacity.h
+    i64p = C.POINTER(C.c_int64)
+    L.b200_interpn.restype = C.c_int
+    L.b200_interpn.argtypes = [vp, C.c_long, C.c_long, vp, vp, i64p, C.c_int, C.c_int, vp, vp]
+    L.b200_aerosol_optics.restype = C.c_int
+    L.b200_aerosol_optics.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.b200_rfm_optics.restype = C.c_int
+    L.b200_rfm_optics.argtypes = [vp, vp, i64p, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.b200_layer2level.restype = C.c_int
+    L.b200_layer2level.argtypes = [vp, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    L.b200_band_optics.restype = C.c_int
+    L.b200_band_optics.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   vp, vp]
     _lib = L
     return L
 

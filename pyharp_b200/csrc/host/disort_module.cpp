@@ -8,10 +8,23 @@
 #include <b200disort.h>
 
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <sstream>
 
 namespace disort {
+
+// Debug aid: with B200DISORT_DUMP=<file> every forward() appends its inputs and result as raw records
+// "<name> <ndim> <dims...>\n" + float64 payload (tests/golden/make_golden_amars.py reads them).  This is how
+// the real amars_sw inputs (tables + profile exactly as examples/amars_sw.cpp builds them) become a fixture.
+static void dump_tensor(std::FILE* f, const char* name, torch::Tensor t) {
+  t = t.to(torch::kCPU, torch::kDouble).contiguous();
+  std::fprintf(f, "%s %d", name, (int)t.dim());
+  for (int64_t d : t.sizes()) std::fprintf(f, " %lld", (long long)d);
+  std::fprintf(f, "\n");
+  std::fwrite(t.data_ptr<double>(), sizeof(double), (size_t)t.numel(), f);
+}
 
 DisortOptions::DisortOptions() {
   std::memset(&ds_, 0, sizeof(ds_));
@@ -165,6 +178,17 @@ torch::Tensor DisortImpl::forward(torch::Tensor prop, std::map<std::string, torc
                 ", status ", first >= 0 ? status_.flatten()[first].item<int>() : -1, ")");
   }
   TORCH_CHECK(rc == B200DISORT_OK, "disort: solve failed: ", b200disort_strerror(rc));
+  if (const char* path = std::getenv("B200DISORT_DUMP")) {
+    if (std::FILE* f = std::fopen(path, "ab")) {
+      std::fprintf(f, "forward %s nstr %d\n", options.flags().c_str(), d.nstr);
+      dump_tensor(f, "prop", prop);
+      if (bc)
+        for (auto const& [key, val] : *bc) dump_tensor(f, ("bc_" + key).c_str(), val);
+      if (temf.has_value()) dump_tensor(f, "temf", *temf);
+      dump_tensor(f, "flx", flx);
+      std::fclose(f);
+    }
+  }
   return flx;
 }
 

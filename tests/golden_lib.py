@@ -7,7 +7,9 @@ import numpy as np
 from pyharp_b200 import workloads as W
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+# solver fixtures (make_golden.py, make_golden_amars.py); opacity_*.npz belong to make_golden_opacity.py
+NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
+               if not os.path.basename(p).startswith("opacity_"))
 
 
 def load(name):

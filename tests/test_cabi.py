@@ -11,10 +11,10 @@ from pyharp_b200 import _cabi
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_functions():
-    src = open(os.path.join(ROOT, "include", "b200disort.h")).read()
+def declared_functions(header="b200disort.h", prefix="b200disort_"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(b200disort_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(" + prefix + r"[a-z0-9_]+)\s*\(", src)))
 
 
 def test_header_symbols_exported():
@@ -24,6 +24,10 @@ def test_header_symbols_exported():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/b200disort.h but not exported"
     assert sorted(_cabi.EXPORTS) == names
+    onames = declared_functions("b200opacity.h", "b200_")
+    assert len(onames) == 5 and sorted(_cabi.OPACITY_EXPORTS) == onames
+    for n in onames:
+        assert hasattr(lib, n), f"{n} declared in include/b200opacity.h but not exported"
 
 
 def test_flag_values_match_header():

@@ -82,3 +82,19 @@ def test_reduce_band(cuda_device):
     got = ds.reduce_band(flx, w).cpu()
     want = (flx.cpu() * w.view(-1, 1, 1, 1)).sum(0)
     assert torch.allclose(got, want, rtol=1e-13, atol=0)
+
+
+import golden_lib as G  # noqa: E402
+
+
+@pytest.mark.parametrize("name", G.NAMES)
+def test_golden_fixtures(cuda_device, name):
+    """Committed fixtures: extended-precision oracle, independent numpy solve, and (amars_sw_real) the real
+    inputs of the reference's examples/amars_sw.cpp."""
+    wl, ld, ind, valid = G.load(name)
+    ds = Disort(wl.options())
+    t = lambda a: None if a is None else torch.from_numpy(a).to(cuda_device)
+    flx = ds.forward(t(wl.prop), {k: t(v) for k, v in wl.bc.items()}, t(wl.temf)).cpu().numpy()
+    assert G.relerr(flx, ld) < RTOL
+    if ind is not None:
+        assert G.relerr(flx, ind, valid) < RTOL
