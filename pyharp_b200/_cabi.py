@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200disort.so")
+LIB_PATH = os.environ.get("B200DISORT_LIB", os.path.join(_HERE, "libb200disort.so"))  # env override: kernel experiments
 
 USRTAU, USRANG, LAMBER, PLANCK, ONLYFL = 1, 2, 4, 8, 16
 INTENSITY_CORRECTION, OLD_INTENSITY_CORRECTION, QUIET = 32, 64, 128

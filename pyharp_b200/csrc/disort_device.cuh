@@ -35,7 +35,9 @@
 #if defined(__CUDA_ARCH__)
 #define B200_RCP(x) __drcp_rn(x)
 #define B200_RSQRT(x) rsqrt(x)
+#define B200_PREFETCH(ptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr))
 #else
+#define B200_PREFETCH(ptr) ((void)0)
 #define B200_RCP(x) (1.0 / (x))
 #define B200_RSQRT(x) (1.0 / sqrt(x))
 #endif

@@ -11,7 +11,22 @@ namespace {
 
 __constant__ QuadTables c_qt;
 
-__global__ void __launch_bounds__(128) disort_flux_kernel(SolveParams p) {
+// resident CTAs per SM asked of ptxas: the small stream counts are latency / bandwidth bound and want warps
+// (128 registers per thread), the larger ones want every register they can get
+#ifndef B200_MIN_BLOCKS
+#define B200_MIN_BLOCKS 0
+#endif
+#if B200_MIN_BLOCKS == 0
+#undef B200_MIN_BLOCKS
+#if B200_NN <= 2
+#define B200_MIN_BLOCKS 4
+#elif B200_NN == 3
+#define B200_MIN_BLOCKS 2
+#else
+#define B200_MIN_BLOCKS 1
+#endif
+#endif
+__global__ void __launch_bounds__(128, B200_MIN_BLOCKS) disort_flux_kernel(SolveParams p) {
   const long nthreads = (long)gridDim.x * blockDim.x;
   const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long nsolve = p.nlocal;
