@@ -343,7 +343,7 @@ static int launch_flux(b200disort_handle* h, SolveParams& p, cudaStream_t stream
   // tuning knobs (profiling only): B200DISORT_BLOCK = threads per CTA (<= 128), B200DISORT_CTAS_PER_SM caps residency
   static const int env_block = std::getenv("B200DISORT_BLOCK") ? std::atoi(std::getenv("B200DISORT_BLOCK")) : 0;
   static const int env_ctas = std::getenv("B200DISORT_CTAS_PER_SM") ? std::atoi(std::getenv("B200DISORT_CTAS_PER_SM")) : 0;
-  const int block = (env_block >= 32 && env_block <= 128) ? env_block : 128;
+  const int block = (env_block >= 32 && env_block <= inst->max_threads) ? env_block : 128;
   if (h->occ == 0) {
     int occ = 0;
     CU_TRY(inst->occupancy(block, &occ));
@@ -602,7 +602,7 @@ extern "C" int b200disort_solve_host(b200disort_handle* h, const double* prop, i
     CU_TRY(h->inst->occupancy(128, &occ));
     h->occ = occ < 1 ? 1 : occ;
   }
-  const long wave = (long)h->sm_count * h->occ * 128;
+  const long wave = (long)h->sm_count * h->occ * 128;  // (launch_flux may be told another CTA size by the tuning knobs)
   const long chunk = std::min(nsolve, wave);
   const long nchunk = (nsolve + chunk - 1) / chunk;
   const size_t in_per = (size_t)c.nlyr * nprop + n_bc;  // doubles per solve

@@ -1,5 +1,11 @@
 // flux_inst.cu -- one instantiation of K1 (the DISORT flux solve kernel) for nn = B200_NN
 // streams per hemisphere.  One thread = one (wave, column) solve; grid-stride over solves.
+#ifndef B200_NN
+#error "compile with -DB200_NN=<nstr/2>"
+#endif
+#ifndef B200_LOCKSTEP
+#define B200_LOCKSTEP (B200_NN >= 6)
+#endif
 #include "flux_inst.cuh"
 
 #ifndef B200_NN
@@ -26,11 +32,22 @@ __constant__ QuadTables c_qt;
 #define B200_MIN_BLOCKS 1
 #endif
 #endif
-__global__ void __launch_bounds__(128, B200_MIN_BLOCKS) disort_flux_kernel(SolveParams p) {
+#if B200_NN <= 2
+#define B200_MAX_THREADS 128
+#else
+#define B200_MAX_THREADS 256
+#endif
+__global__ void __launch_bounds__(B200_MAX_THREADS, B200_MIN_BLOCKS) disort_flux_kernel(SolveParams p) {
   const long nthreads = (long)gridDim.x * blockDim.x;
   const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long nsolve = p.nlocal;
-  for (long s = tid; s < nsolve; s += nthreads) solve_flux_one<B200_NN>(p, c_qt, s, tid);
+  // CTA-uniform trip count: the solver contains CTA barriers (lockstep walk); threads beyond the end of the
+  // batch shadow the last solve and write nothing
+  for (long base = (long)blockIdx.x * blockDim.x; base < nsolve; base += nthreads) {
+    const long s = base + threadIdx.x;
+    const bool active = s < nsolve;
+    solve_flux_one<B200_NN>(p, c_qt, active ? s : nsolve - 1, tid, active);
+  }
 }
 
 cudaError_t upload_tables(const QuadTables* qt) { return cudaMemcpyToSymbol(c_qt, qt, sizeof(QuadTables)); }
@@ -44,7 +61,7 @@ cudaError_t launch(const SolveParams& p, unsigned grid, int block, cudaStream_t 
   return cudaGetLastError();
 }
 
-const FluxInst kInst = {B200_NN, B200_NN * B200_NN + 2 * B200_NN + 1, upload_tables, occupancy, launch};
+const FluxInst kInst = {B200_NN, B200_NN * B200_NN + 2 * B200_NN + 1, B200_MAX_THREADS, upload_tables, occupancy, launch};
 
 }  // namespace
 

@@ -11,6 +11,7 @@ namespace b200 {
 struct FluxInst {
   int nn;
   int nsave;  // doubles stored per level and solve for the back sweep
+  int max_threads;  // __launch_bounds__ of the kernel
   cudaError_t (*upload_tables)(const QuadTables*);
   cudaError_t (*occupancy)(int block, int* blocks_per_sm);
   cudaError_t (*launch)(const SolveParams&, unsigned grid, int block, cudaStream_t);
