@@ -300,6 +300,12 @@ def main():
         hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
         fp64_peak = fp64_peak_tflops(local)
         W_, Q_ = wl.flops_per_solve(), wl.bytes_per_solve()
+        traffic = None
+        try:  # DRAM bytes per launch of the solve kernel from the committed ncu --set full capture of this workload
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01", "traffic.json")))[args.workload]
+            traffic = tr["bytes_per_launch"] / tr["solves_per_launch"] * wl.nsolve
+        except Exception:  # noqa: BLE001
+            pass
         ach_tf = W_ * wl.nsolve / (kernel_ms * 1e-3) / 1e12
         ach_gbs = Q_ * wl.nsolve / (kernel_ms * 1e-3) / 1e9
         out = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
@@ -310,11 +316,13 @@ def main():
                "kernel": {"name": "disort_flux_kernel", "avg_ms": kernel_ms, "share_of_step": kernel_ms / (ms / args.steps),
                           "workspace_bytes": st["workspace_bytes"]},
                "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                            "frac": ach_tf / fp64_peak, "traffic": None,
+                            "frac": ach_tf / fp64_peak, "traffic": traffic,
                             "peak_source": "DFMA-saturating kernel measured in this run (b200disort_fp64_peak); "
                                            "profiles/microbench/fp64_peak_r01.json has the sweep",
-                            "note": "achieved = reference-algorithm flop count W x solves / kernel time; the adding-"
-                                    "method kernel executes fewer flops than W (see DESIGN.md)"},
+                            "note": "achieved = reference-algorithm flop count W (SURVEY.md 8d) x solves / kernel time. "
+                                    "The adding-method kernel executes ~1/3 of W (ncu: profiles/r01/ncu_full_*_summary.txt, "
+                                    "FP64 pipe 46 % active on this workload), so frac can exceed 1; traffic = DRAM bytes per "
+                                    "launch from the committed ncu capture (back-sweep workspace dominates)"},
                "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                                 "frac": ach_gbs / hbm_peak, "peak_source": hbm_src},
                "e2e": e2e}
