@@ -13,6 +13,7 @@
  *                           branch there is an empty stub)
  *   b200_rfm_optics      <- RFMImpl::forward + get_reftemp (src/opacity/rfm.cpp:122-197)
  *   b200_layer2level     <- harp::layer2level (src/utils/layer2level.cpp:7-79)
+ *   b200_spherical_flux_correction <- harp::spherical_flux_correction (src/utils/spherical_flux_correction.cpp:3-18)
  *   b200_band_optics     <- the optical-property mixing the examples do before the solve
  *                           (examples/amars_sw.cpp:262-273; RadiationBandImpl::forward
  *                           src/radiation/radiation_band.cpp:83-116 in the 4-D layout)
@@ -60,6 +61,13 @@ int b200_layer2level(const double* var, long nrow, int nlyr, int order, int blow
  * att / nprops are HOST arrays of device pointers / ints. */
 int b200_band_optics(const double* const* att, const int* nprops, int natt, const double* dz, int nwave, int ncol,
                      int nlyr, int nprop_out, double* prop, void* stream);
+
+/* harp::spherical_flux_correction (src/utils/spherical_flux_correction.cpp:3-18), in place on
+ * flx (nrow, nx1): x1f[nx1] interface coordinates, area / vol (nrow, nx1).  Walks down from the top level;
+ * like the reference (whose `flx_iu` is a view of the tensor it then overwrites) the divergence at level i
+ * uses the already corrected flux of level i+1. */
+int b200_spherical_flux_correction(double* flx, const double* x1f, const double* area, const double* vol, long nrow,
+                                   int nx1, void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,6 +11,7 @@
 #include <opacity/rfm.hpp>
 #include <opacity/s8_fuller.hpp>
 #include <utils/layer2level.hpp>
+#include <utils/spherical_flux_correction.hpp>
 
 static torch::Tensor wrapd(const double* p, std::vector<int64_t> shape) {
   return torch::from_blob(const_cast<double*>(p), shape, torch::kFloat64).clone();
@@ -90,6 +91,19 @@ extern "C" int ref_layer2level(const double* var, long nrow, int nlyr, int order
     return 0;
   } catch (std::exception const& e) {
     std::fprintf(stderr, "ref_layer2level: %s\n", e.what());
+    return 2;
+  }
+}
+
+extern "C" int ref_spherical_flux_correction(double* flx, const double* x1f, const double* area, const double* vol,
+                                             long nrow, int nx1) {
+  try {
+    auto f = wrapd(flx, {nrow, nx1});
+    auto res = spherical_flux_correction(f, wrapd(x1f, {nx1}), wrapd(area, {nrow, nx1}), wrapd(vol, {nrow, nx1})).contiguous();
+    std::memcpy(flx, res.data_ptr<double>(), sizeof(double) * res.numel());
+    return 0;
+  } catch (std::exception const& e) {
+    std::fprintf(stderr, "ref_spherical_flux_correction: %s\n", e.what());
     return 2;
   }
 }

@@ -38,7 +38,8 @@ EXPORTS = ("b200disort_create", "b200disort_solve", "b200disort_solve_host",
            "b200disort_check_status", "b200disort_get_rad", "b200disort_reduce_band",
            "b200disort_get_stats", "b200disort_fp64_peak", "b200disort_destroy",
            "b200disort_strerror", "b200disort_version")
-OPACITY_EXPORTS = ("b200_interpn", "b200_aerosol_optics", "b200_rfm_optics", "b200_layer2level", "b200_band_optics")
+OPACITY_EXPORTS = ("b200_interpn", "b200_aerosol_optics", "b200_rfm_optics", "b200_layer2level", "b200_band_optics",
+                   "b200_spherical_flux_correction")
 
 _lib = None
 
@@ -85,6 +86,8 @@ def lib():
     L.b200_rfm_optics.argtypes = [vp, vp, i64p, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
     L.b200_layer2level.restype = C.c_int
     L.b200_layer2level.argtypes = [vp, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    L.b200_spherical_flux_correction.restype = C.c_int
+    L.b200_spherical_flux_correction.argtypes = [vp, vp, vp, vp, C.c_long, C.c_int, vp]
     L.b200_band_optics.restype = C.c_int
     L.b200_band_optics.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                    vp, vp]

@@ -138,6 +138,24 @@ __global__ void layer2level_kernel(const double* __restrict__ var, long nrow, in
   }
 }
 
+// one thread per row (column x band ...); the recurrence runs down the levels
+__global__ void spherical_flux_kernel(double* __restrict__ flx, const double* __restrict__ x1f, const double* __restrict__ area,
+                                      const double* __restrict__ vol, long nrow, int nx1) {
+  for (long r = (long)blockIdx.x * blockDim.x + threadIdx.x; r < nrow; r += (long)gridDim.x * blockDim.x) {
+    double* f = flx + r * nx1;
+    const double* a = area + r * nx1;
+    const double* v = vol + r * nx1;
+    double fiu = f[nx1 - 1];
+    for (int i = nx1 - 2; i >= 0; --i) {
+      const double dx = __dsub_rn(x1f[i + 1], x1f[i]);
+      const double volh = __dmul_rn(__ddiv_rn(__dsub_rn(fiu, f[i]), dx), v[i]);
+      const double nf = __ddiv_rn(__dsub_rn(__dmul_rn(f[i + 1], a[i + 1]), volh), a[i]);
+      f[i] = nf;
+      fiu = nf;  // the reference's flx_iu aliases flx[..., i] after the assignment
+    }
+  }
+}
+
 constexpr int kMaxAtt = 8;
 struct AttList {
   const double* p[kMaxAtt];
@@ -249,5 +267,12 @@ extern "C" int b200_band_optics(const double* const* att, const int* nprops, int
   for (int t = 0; t < natt; ++t) { a.p[t] = att[t]; a.nprop[t] = nprops[t]; if (!att[t] || nprops[t] < 1) return 1; }
   const long npoint = (long)nwave * ncol * nlyr;
   band_optics_kernel<<<grid_for(npoint, 256), 256, 0, (cudaStream_t)stream>>>(a, dz, npoint, nlyr, nprop_out, prop);
+  return cudaGetLastError() == cudaSuccess ? 0 : 2;
+}
+
+extern "C" int b200_spherical_flux_correction(double* flx, const double* x1f, const double* area, const double* vol, long nrow,
+                                              int nx1, void* stream) {
+  if (!flx || !x1f || !area || !vol || nrow < 1 || nx1 < 2) return 1;
+  spherical_flux_kernel<<<grid_for(nrow, 128), 128, 0, (cudaStream_t)stream>>>(flx, x1f, area, vol, nrow, nx1);
   return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }

@@ -214,3 +214,20 @@ def band_optics(attenuations, dz):
                                           _stream())
     _check(rc, "b200_band_optics")
     return out
+
+
+def spherical_flux_correction(flx, x1f, area, vol):
+    """harp::spherical_flux_correction (src/utils/spherical_flux_correction.cpp:3-18) on the GPU, in place on a
+    contiguous CUDA tensor flx (..., nx1); x1f (nx1,), area / vol (..., nx1).  Returns flx."""
+    if not (flx.is_cuda and flx.is_contiguous() and flx.dtype == torch.float64):
+        raise RuntimeError("spherical_flux_correction: contiguous float64 CUDA tensor required (no CPU fallback)")
+    nx1 = x1f.shape[0]
+    if flx.shape[-1] != nx1:
+        raise ValueError("flx's last dimension must match x1f")
+    dev = flx.device
+    x1f, area, vol = _dev(x1f, dev), _dev(area, dev).expand_as(flx).contiguous(), _dev(vol, dev).expand_as(flx).contiguous()
+    with torch.cuda.device(dev):
+        rc = _cabi.lib().b200_spherical_flux_correction(flx.data_ptr(), x1f.data_ptr(), area.data_ptr(), vol.data_ptr(),
+                                                        flx.numel() // nx1, nx1, _stream())
+    _check(rc, "b200_spherical_flux_correction")
+    return flx

@@ -110,6 +110,48 @@ TEST(Shim, bad_input_throws) {
   EXPECT_THROW(disort::Disort d2(op2), c10::Error);
 }
 
+// harp::call_interpn_cuda<N> (declared at src/math/interpolation.hpp:12-14, defined in
+// pyharp_b200/csrc/host/harp_cuda_dispatch.cpp), driven by a TensorIterator built the way
+// S8FullerImpl::forward builds it (src/opacity/s8_fuller.cpp:88-103)
+namespace harp {
+template <int N>
+void call_interpn_cuda(at::TensorIterator& iter, at::Tensor kdata, at::Tensor axis, at::Tensor dims, int nval);
+}
+
+TEST(Shim, call_interpn_cuda_like_s8fuller) {
+  const int nwave = 7, ncol = 2, nlyr = 3, nprop = 2, rows = 9;
+  auto dev = torch::Device(torch::kCUDA, 0);
+  auto kwave = torch::linspace(0.2, 5.0, rows, torch::kFloat64);
+  auto kdata = torch::rand({rows, nprop}, torch::kFloat64);
+  auto coord = torch::tensor({0.1, 0.2, 0.77, 1.4, 3.3, 5.0, 9.0}, torch::kFloat64);
+  auto out = torch::zeros({nwave, ncol, nlyr, nprop}, torch::TensorOptions().dtype(torch::kFloat64).device(dev));
+  auto dims = torch::tensor({rows}, torch::TensorOptions().dtype(torch::kInt64).device(dev));
+  auto iter = at::TensorIteratorConfig()
+                  .resize_outputs(false)
+                  .check_all_same_dtype(true)
+                  .declare_static_shape(out.sizes(), /*squash_dims=*/3)
+                  .add_output(out)
+                  .add_owned_const_input(coord.to(dev).view({-1, 1, 1, 1}).expand({-1, ncol, nlyr, nprop}))
+                  .build();
+  harp::call_interpn_cuda<2>(iter, kdata.to(dev), kwave.to(dev), dims, nprop);
+  auto got = out.cpu();
+  auto kw = kwave.accessor<double, 1>();
+  auto kd = kdata.accessor<double, 2>();
+  for (int w = 0; w < nwave; ++w) {
+    const double x = coord[w].item<double>();
+    int i1 = 0;
+    while (i1 + 1 < rows - 1 && kw[i1 + 1] <= x) ++i1;
+    for (int j = 0; j < nprop; ++j) {
+      double want;
+      if (x <= kw[0]) want = kd[0][j];
+      else if (x >= kw[rows - 1]) want = kd[rows - 1][j];
+      else want = ((x - kw[i1]) * kd[i1 + 1][j] + (kw[i1 + 1] - x) * kd[i1][j]) / (kw[i1 + 1] - kw[i1]);
+      for (int c = 0; c < ncol; ++c)
+        for (int l = 0; l < nlyr; ++l) EXPECT_NEAR(got[w][c][l][j].item<double>(), want, 1e-15);
+    }
+  }
+}
+
 int main(int argc, char** argv) {
   testing::InitGoogleTest(&argc, argv);
   return RUN_ALL_TESTS();

@@ -84,6 +84,14 @@ def main():
                 for bu in (0, 1):
                     d[f"out{nlyr}_o{order}_l{bl}_u{bu}"] = R.layer2level(var, order, bl, bu)
     np.savez_compressed(os.path.join(HERE, "opacity_layer2level.npz"), **d)
+    nrow, nx1 = 6, 21
+    x1f = np.cumsum(r.uniform(500.0, 1500.0, nx1))
+    rad = 3.39e6 + x1f
+    area = np.tile(rad ** 2, (nrow, 1)) * r.uniform(0.99, 1.01, (nrow, 1))
+    vol = area * np.gradient(x1f)[None, :]
+    flx = r.uniform(10.0, 400.0, (nrow, nx1))
+    np.savez_compressed(os.path.join(HERE, "opacity_spherical.npz"), flx=flx, x1f=x1f, area=area, vol=vol,
+                        out=R.spherical_flux_correction(flx, x1f, area, vol))
     print("written:", [f for f in sorted(os.listdir(HERE)) if f.startswith("opacity_")])
 
 

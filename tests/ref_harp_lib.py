@@ -73,3 +73,10 @@ def layer2level(var, order=4, blower=0, bupper=1):
     rc = lib().ref_layer2level(_p(var), C.c_long(var.shape[0]), var.shape[1], order, blower, bupper, _p(out))
     assert rc == 0
     return out
+
+
+def spherical_flux_correction(flx, x1f, area, vol):
+    flx, x1f, area, vol = _d(flx).copy(), _d(x1f), _d(area), _d(vol)
+    rc = lib().ref_spherical_flux_correction(_p(flx), _p(x1f), _p(area), _p(vol), C.c_long(flx.shape[0]), flx.shape[1])
+    assert rc == 0
+    return flx

@@ -23,7 +23,7 @@ def _run(exe, cwd=None):
 
 def test_cpp_shim(cuda_device):
     out = _run("test_shim")
-    assert "4 tests ran, 0 failed" in out
+    assert "5 tests ran, 0 failed" in out
 
 
 def test_reference_test_disort_unchanged(cuda_device):
@@ -46,3 +46,14 @@ def test_reference_amars_sw_unchanged(cuda_device):
     dt = np.loadtxt(os.path.join(run, "dT_ds.txt"), comments="#")
     assert np.isfinite(dt).all() and dt.shape[0] >= 39
     assert "nan" not in out.lower()
+
+
+def test_reference_radiation_band_holds_our_solver(cuda_device):
+    """harp::Radiation / RadiationBand / S8Fuller compiled unchanged from the reference, with this repo's
+    disort::Disort as the band's rtsolver AnyModule (tests/cpp/ref_radiation_band.cpp)."""
+    if not os.path.exists(os.path.join(BUILD, "ref_radiation_band")):
+        pytest.skip("reference drivers were not built (no /root/reference at build time)")
+    out = _run("ref_radiation_band", cwd=os.path.join(BUILD, "run"))
+    assert "RADIATION_BAND_OK" in out and "Solver: disort" in out
+    toa = float(re.search(r"toa_down_mean = ([-0-9.e+]+)", out).group(1))
+    assert abs(toa - 1.0) < 1e-12  # mu0 * fbeam at the top of the atmosphere

@@ -96,3 +96,10 @@ def test_optics_feed_the_solver_on_device(cuda_device):
                             flags=O.LAMBER | O.ONLYFL)
     assert not st.any()
     assert G.relerr(flx.cpu().numpy(), want) < 1e-9
+
+
+def test_spherical_flux_correction_bit_exact(cuda_device):
+    z = _load("opacity_spherical.npz")
+    flx = torch.from_numpy(z["flx"]).to(cuda_device).contiguous()
+    got = OP.spherical_flux_correction(flx, z["x1f"], z["area"], z["vol"]).cpu().numpy()
+    assert np.array_equal(got, z["out"])

@@ -49,3 +49,8 @@ def test_aerosol_tables_parsed_like_the_reference():
         assert np.array_equal(tab[:, 0], z[kind + "_kwave"])
         assert np.array_equal(tab[:, 1] * z["species_weights"][sid], z[kind + "_kdata"][:, 0])
         assert np.array_equal(tab[:, 2], z[kind + "_kdata"][:, 1])
+
+
+def test_spherical_fixture_is_reference_output():
+    z = _load("opacity_spherical.npz")
+    assert np.array_equal(R.spherical_flux_correction(z["flx"], z["x1f"], z["area"], z["vol"]), z["out"])
