@@ -152,6 +152,13 @@ B200_HD double plkavg(double wnumlo, double wnumhi, double t) {
 // packed lower-triangular index (i >= j)
 B200_HD constexpr int sym(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
 
+// thread-private array in shared memory, element e of this thread at base[e * stride]
+struct SmemArray {
+  double* base;
+  int stride;
+  B200_HD double& operator[](int e) const { return base[(long)e * stride]; }
+};
+
 constexpr int kMaxSweeps = 16;
 
 // Brent-Luk tournament: data source of position i after one round (n even; pairs are (2k, 2k+1))

@@ -6,6 +6,11 @@
 #ifndef B200_LOCKSTEP
 #define B200_LOCKSTEP (B200_NN >= 6)
 #endif
+// parking the stack state (Ra, da) in shared memory instead of letting ptxas spill it: measured -5 % at nstr = 16
+// (5.0 vs 5.3 M solves/s), so it is off; -DB200_SMEM_STACK=1 turns it on for experiments
+#ifndef B200_SMEM_STACK
+#define B200_SMEM_STACK 0
+#endif
 #include "flux_inst.cuh"
 
 #ifndef B200_NN
@@ -52,12 +57,27 @@ __global__ void __launch_bounds__(B200_MAX_THREADS, B200_MIN_BLOCKS) disort_flux
 
 cudaError_t upload_tables(const QuadTables* qt) { return cudaMemcpyToSymbol(c_qt, qt, sizeof(QuadTables)); }
 
+// dynamic shared memory per CTA: the parked stack state (Ra packed symmetric + da) of every thread
+size_t smem_bytes(int block) {
+#if B200_SMEM_STACK
+  return (size_t)(B200_NN * (B200_NN + 1) / 2 + B200_NN) * block * sizeof(double);
+#else
+  (void)block;
+  return 0;
+#endif
+}
+
 cudaError_t occupancy(int block, int* blocks_per_sm) {
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, disort_flux_kernel, block, 0);
+  const size_t sm = smem_bytes(block);
+  if (sm > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(disort_flux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, disort_flux_kernel, block, sm);
 }
 
 cudaError_t launch(const SolveParams& p, unsigned grid, int block, cudaStream_t stream) {
-  disort_flux_kernel<<<grid, block, 0, stream>>>(p);
+  disort_flux_kernel<<<grid, block, smem_bytes(block), stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -98,3 +98,34 @@ def test_golden_fixtures(cuda_device, name):
     assert G.relerr(flx, ld) < RTOL
     if ind is not None:
         assert G.relerr(flx, ind, valid) < RTOL
+
+
+@pytest.mark.parametrize("nstr", [2, 4, 6, 8, 12, 16, 24, 32])
+@pytest.mark.parametrize("thermal", [False, True])
+def test_every_stream_count(cuda_device, nstr, thermal):
+    """All K1 instantiations (nn = 1, 2, 3, 4, 6, 8, 12, 16), beam + Lambertian surface, optionally thermal, with
+    Henyey-Greenstein phase functions truncated by delta-M."""
+    rng = np.random.default_rng(100 + nstr + int(thermal))
+    nw, nc, nl = 3, 5, 9
+    prop = np.zeros((nw, nc, nl, 2 + nstr))
+    prop[..., 0] = 10.0 ** rng.uniform(-3, 0.4, (nw, nc, nl))
+    prop[..., 1] = rng.uniform(0.0, 0.999, (nw, nc, nl))
+    g = rng.uniform(0.0, 0.85, (nw, nc, nl))
+    for k in range(nstr):
+        prop[..., 2 + k] = g ** (k + 1)
+    bc = {"fbeam": rng.uniform(1, 4, (nw, nc)), "umu0": rng.uniform(0.15, 0.95, (nw, nc)), "albedo": rng.uniform(0, 1, (nw, nc))}
+    x, _ = np.polynomial.legendre.leggauss(nstr // 2)
+    for q in 0.5 * (x + 1):  # keep the beam off the quadrature angles
+        bc["umu0"] = np.where(np.abs(bc["umu0"] - q) / bc["umu0"] < 1e-3, bc["umu0"] * 1.01, bc["umu0"])
+    tokens, temf, kw = "lamber,quiet,onlyfl", None, {}
+    if thermal:
+        tokens += ",planck"
+        temf = np.linspace(290.0, 180.0, nl + 1)[None, :].repeat(nc, 0)
+        bc.update(btemp=np.full((nw, nc), 295.0), ttemp=np.full((nw, nc), 120.0), temis=np.full((nw, nc), 0.3))
+        kw = dict(wave_lower=np.array([100.0, 600.0, 1500.0]), wave_upper=np.array([600.0, 1500.0, 1510.0]))
+    wl = W.Workload("streams", nstr, tokens, prop, bc, temf, kw.get("wave_lower"), kw.get("wave_upper"))
+    ref = _oracle(wl)
+    ds = Disort(wl.options())
+    t = lambda a: None if a is None else torch.from_numpy(a).to(cuda_device)
+    flx = ds.forward(t(prop), {k: t(v) for k, v in bc.items()}, t(temf)).cpu().numpy()
+    assert _relerr(flx, ref) < RTOL
