@@ -1491,6 +1491,14 @@ int orc_disort(const orc_problem* pb, const double* dtauc_in, const double* ssal
                  !(pb->ttemp >= 0.0) || !(pb->temis >= 0.0 && pb->temis <= 1.0)))
     return ST_BAD_INPUT;
 
+  /* DISORT main program: "IF( SSALB(LC).EQ.1.0 ) SSALB(LC) = 1.0 - DITHER" with DITHER = max(10 eps, 1e-10):
+     an exactly conservative layer would give a zero eigenvalue */
+  double* ssalb_d = (double*)malloc(sizeof(double) * nlyr);
+  for (int lc = 0; lc < nlyr; ++lc) ssalb_d[lc] = (ssalb_in[lc] == 1.0) ? 1.0 - 1.0e-10 : ssalb_in[lc];
+  const double* ssalb_orig = ssalb_in;
+  (void)ssalb_orig;
+  ssalb_in = ssalb_d;
+
   work W;
   work* w = &W;
   memset(w, 0, sizeof(W));
@@ -1788,6 +1796,7 @@ cleanup:
   free(w->zj); free(w->z0); free(w->z1); free(w->cc); free(w->amb); free(w->apb); free(w->arr);
   free(w->evecc); free(w->eval); free(w->cband); free(w->b); free(w->u0c); free(w->uum);
   free(w->wk); free(phirad); free(uur);
+  free(ssalb_d);
   return status;
 }
 

@@ -483,8 +483,10 @@ B200_FN_ATTR inline void solve_intensity_one(const IntensityParams& P, long s, d
     w[M.expbea] = (fbeam > 0.0) ? 1.0 : 0.0;
     for (int lc = 0; lc < L; ++lc) {
       const double* q = pr + (long)(L - 1 - lc) * nprop;
-      const double dtau = q[0], ssa = (nprop > 1) ? q[1] : 0.0;
+      double ssa = (nprop > 1) ? q[1] : 0.0;
+      const double dtau = q[0];
       if (!(dtau >= 0.0) || !(ssa >= 0.0 && ssa <= 1.0)) st = ST_BAD_INPUT;
+      if (ssa == 1.0) ssa = 1.0 - 1.0e-10;  // DISORT's dither of exactly conservative layers
       for (int k = 1; k <= P.nmom; ++k) {
         const double pm = prop_pmom(pr, L, nprop, lc, k);
         if (!(pm >= -1.0 && pm <= 1.0)) st = ST_BAD_INPUT;

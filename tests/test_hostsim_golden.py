@@ -121,3 +121,50 @@ def test_status_codes():
     wl.bc["umu0"][:] = 0.5 * (x[2] + 1)
     _, st = _sim(wl)
     assert st[0, 0] == 5
+
+
+def _edge_problem(nstr, nl, ssa=None, zero_layers=(), thermal=False, seed=5):
+    rng = np.random.default_rng(seed)
+    nw, nc = 2, 3
+    prop = np.zeros((nw, nc, nl, 2 + nstr))
+    prop[..., 0] = 10 ** rng.uniform(-1, 0.5, (nw, nc, nl))
+    prop[..., 1] = rng.uniform(0, 0.99, (nw, nc, nl)) if ssa is None else ssa
+    g = rng.uniform(0, 0.8, (nw, nc, nl))
+    for k in range(nstr):
+        prop[..., 2 + k] = g ** (k + 1)
+    for z in zero_layers:
+        prop[:, :, z, 0] = 0.0
+    bc = {"fbeam": np.full((nw, nc), 2.0), "umu0": np.full((nw, nc), 0.62), "albedo": np.full((nw, nc), 0.3)}
+    flags, temf, kw = O.LAMBER | O.ONLYFL, None, {}
+    if thermal:
+        flags |= O.PLANCK
+        temf = np.linspace(300, 200, nl + 1)[None, :].repeat(nc, 0)
+        bc["btemp"] = np.full((nw, nc), 300.0)
+        kw = dict(wave_lower=np.full(nw, 500.0), wave_upper=np.full(nw, 700.0))
+    return prop, bc, temf, flags, kw
+
+
+@pytest.mark.parametrize("thermal", [False, True])
+def test_layers_of_zero_optical_depth(thermal):
+    prop, bc, temf, flags, kw = _edge_problem(8, 6, zero_layers=(0, 3, 5), thermal=thermal)
+    ref, _, st = O.forward(prop, bc, temf, nstr=8, flags=flags, **kw)
+    got, st2 = H.flux(prop, bc, temf, nstr=8, flags=flags, **kw)
+    assert not st.any() and not st2.any()
+    assert G.relerr(got, ref) < RTOL
+    # a layer without optical depth changes nothing: the fluxes on its two sides are equal
+    np.testing.assert_allclose(got[:, :, 0], got[:, :, 1], rtol=1e-13)
+
+
+def test_conservative_scattering_is_dithered():
+    """ssalb = 1 exactly: DISORT replaces it by 1 - 1e-10 (a zero eigenvalue otherwise).  In that regime the
+    eigenvalue k ~ 1e-5 makes every FP64 formulation lose digits: the FP64 oracle (banded LU, like cdisort) is
+    only ~1e-7 from the extended-precision solve, the adding formulation of the kernels ~1e-9.  Parity is therefore
+    checked against the extended-precision oracle at 1e-8."""
+    prop, bc, temf, flags, kw = _edge_problem(8, 5, ssa=1.0)
+    ld, _, st = O.forward(prop, bc, temf, nstr=8, flags=flags, long_double=True)
+    f64, _, _ = O.forward(prop, bc, temf, nstr=8, flags=flags)
+    got, st2 = H.flux(prop, bc, temf, nstr=8, flags=flags)
+    assert not st.any() and not st2.any()
+    assert G.relerr(got, ld) < 1e-8
+    assert G.relerr(f64, ld) < 1e-5
+    assert np.isfinite(got).all() and (got >= -1e-12).all()
