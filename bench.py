@@ -326,7 +326,7 @@ def main():
                "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                                 "frac": ach_gbs / hbm_peak, "peak_source": hbm_src},
                "e2e": e2e}
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:  # the CPU leg is reported at N = 1 only
             out["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(out), flush=True)
     if world > 1:
