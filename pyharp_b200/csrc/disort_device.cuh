@@ -159,6 +159,13 @@ struct SmemArray {
   B200_HD double& operator[](int e) const { return base[(long)e * stride]; }
 };
 
+// reference to `a` when B, else to `b` (storage-sharing switch in the solver body)
+template <bool B, typename T>
+B200_HD T& pick_ref(T& a, T& b) {
+  if constexpr (B) return a;
+  else return b;
+}
+
 constexpr int kMaxSweeps = 16;
 
 // Brent-Luk tournament: data source of position i after one round (n even; pairs are (2k, 2k+1))
