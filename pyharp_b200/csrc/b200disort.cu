@@ -343,7 +343,7 @@ static int launch_flux(b200disort_handle* h, SolveParams& p, cudaStream_t stream
   // tuning knobs (profiling only): B200DISORT_BLOCK = threads per CTA (<= 128), B200DISORT_CTAS_PER_SM caps residency
   static const int env_block = std::getenv("B200DISORT_BLOCK") ? std::atoi(std::getenv("B200DISORT_BLOCK")) : 0;
   static const int env_ctas = std::getenv("B200DISORT_CTAS_PER_SM") ? std::atoi(std::getenv("B200DISORT_CTAS_PER_SM")) : 0;
-  const int block = (env_block >= 32 && env_block <= inst->max_threads) ? env_block : 128;
+  const int block = (env_block >= 32 && env_block <= inst->max_threads && env_block % 32 == 0) ? env_block : 128;  // whole warps: the workspace is laid out per warp
   if (h->occ == 0) {
     int occ = 0;
     CU_TRY(inst->occupancy(block, &occ));

@@ -33,9 +33,38 @@
 #endif
 
 #if defined(__CUDA_ARCH__)
+// Reciprocal and reciprocal square root without the range check, branch and slow-path call of the CUDA math
+// library versions: MUFU seed (2^-22) plus the same refinement, straight-line.  The library forms end every use
+// in a conditional CALL, which splits the instruction stream into short basic blocks -- independent pivot /
+// rotation chains could not be interleaved across them (ncu: `wait` was the top stall).  Valid for normal,
+// positive-finite arguments only (rsqrt) / normal arguments (rcp); every call site guards its argument
+// (pivots and eigenvalues are checked against kTiny, the other arguments are O(1) by construction).
+#ifndef B200_FAST_RECIP
+#define B200_FAST_RECIP 1
+#endif
+#if B200_FAST_RECIP
+__device__ __forceinline__ double b200_fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+__device__ __forceinline__ double b200_fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x, y * y, 1.0);  // y (1 + e/2 + 3 e^2/8): third order, 2^-22 -> below 2^-53
+  return fma(fma(e, 0.375, 0.5), y * e, y);
+}
+#define B200_RCP(x) b200_fast_rcp(x)
+#define B200_RSQRT(x) b200_fast_rsqrt(x)
+#else
 #define B200_RCP(x) __drcp_rn(x)
 #define B200_RSQRT(x) rsqrt(x)
+#endif
 #define B200_PREFETCH(ptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr))
+#define B200_HIWORD(x) __double2hiint(x)
 // CTA lockstep (see jacobi_spd in disort_solver_body.inc); every thread of the CTA must reach these.
 // Measured on B200: +32 % at nstr = 16 (instruction-fetch bound: 376 KB of unrolled code, I-cache hit rate 51 %),
 // -3..6 % at nstr = 8, so flux_inst.cu enables it from nn = 6 up.
@@ -52,12 +81,24 @@
 #define B200_PREFETCH(ptr) ((void)0)
 #define B200_RCP(x) (1.0 / (x))
 #define B200_RSQRT(x) (1.0 / sqrt(x))
+#define B200_HIWORD(x) b200::host_hiword(x)
+#include <string.h>
+#include <algorithm>
+namespace b200 {
+inline int host_hiword(double x) {
+  long long b;
+  memcpy(&b, &x, 8);
+  return (int)(b >> 32);
+}
+using std::max;
+}  // namespace b200
 #endif
 
 namespace b200 {
 
 constexpr int kMaxNN = 16;  // nstr <= 32
 constexpr double kPi = 3.14159265358979323846;
+constexpr double kTiny = 1.0e-290;  // pivots / eigenvalues at or below this are treated as zero (singular)
 
 // status words (include/b200disort.h)
 enum : int { ST_OK = 0, ST_BAD_INPUT = 1, ST_EIGEN_FAIL = 2, ST_SINGULAR = 3, ST_UNSUPPORTED = 4, ST_BEAM_ANGLE = 5 };
@@ -88,8 +129,8 @@ struct SolveParams {
   int32_t* status; // (nwave,ncol)
   long s0;         // batch index of this launch's first solve (chunked host path); prop/bc/flx/status are chunk-local
   long nlocal;     // solves in this launch
-  double* ws;      // back-sweep workspace: [level][elem][thread]
-  long ws_threads; // number of threads (stride of the fastest workspace axis)
+  double* ws;      // back-sweep workspace: [warp][level][elem][lane] (kWsLanes lanes per group)
+  long ws_threads; // threads the workspace was sized for (a multiple of kWsLanes)
 };
 
 // ---------------------------------------------------------------------------
@@ -167,6 +208,54 @@ B200_HD T& pick_ref(T& a, T& b) {
 }
 
 constexpr int kMaxSweeps = 16;
+#ifndef B200_BS_DEPTH
+#define B200_BS_DEPTH 3
+#endif
+#ifndef B200_OPT_SPD2
+#define B200_OPT_SPD2 1
+#endif
+
+// Back-sweep workspace layout [warp][level][element][lane] (see solve_flux_one): lanes per group.  The host
+// simulator runs one solve at a time (one lane).
+#if defined(__CUDA_ARCH__) || defined(__CUDACC__)
+constexpr int kWsLanes = 32;
+#else
+constexpr int kWsLanes = 1;
+#endif
+constexpr int kWsPrefetchAhead = 4;  // levels between a record's L2 prefetch and its register load
+
+// Prefetch the (warp, level) record -- NSAVE * kWsLanes doubles, contiguous -- one 128-byte line per lane and
+// instruction.  wsl is the lane's own base pointer (it already includes the lane offset).
+template <int NSAVE>
+B200_HD void ws_prefetch_record(const double* wsl, int lev, long tid) {
+#if defined(__CUDA_ARCH__)
+  if (lev < 0) return;
+  const int lane = (int)(tid % kWsLanes);
+  const char* rec = reinterpret_cast<const char*>(wsl - lane + (long)lev * NSAVE * kWsLanes);
+  constexpr int kLines = (NSAVE * kWsLanes * 8 + 127) / 128;
+#pragma unroll
+  for (int l0 = 0; l0 < kLines; l0 += kWsLanes)
+    if (l0 + lane < kLines) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + (long)(l0 + lane) * 128));
+#else
+  (void)wsl; (void)lev; (void)tid;
+#endif
+}
+
+// Jacobi rotation that annihilates g_pq (small-angle root): t = tan, s = sin, c = cos of the angle, from the
+// half-angle identities with two reciprocal square roots -- no sqrt, no division (measured cost of the classical
+// form t = b / (d + sign(d) sqrt(d^2 + b^2)), c = 1/sqrt(1 + t^2), tau = s / (1 + c): 49 DFMA-equivalents, this
+// one: 32).  cos 2a = |d| h >= 0, so x = (1 + cos 2a) / 2 is in [1/2, 1] and nothing cancels.  A pair below the
+// relative threshold gets the identity (d := 1, b := 0), not a branch.
+B200_HD void jacobi_rotation(double gpq, double gpp, double gqq, double eps2, double& t, double& s, double& c) {
+  const bool rot = gpq * gpq > eps2 * fabs(gpp * gqq);
+  const double d = rot ? gqq - gpp : 1.0, b2 = rot ? 2.0 * gpq : 0.0;
+  const double sd = copysign(B200_RSQRT(fma(d, d, b2 * b2)), d);
+  const double x = fma(0.5 * d, sd, 0.5);
+  const double rc = B200_RSQRT(x);
+  c = x * rc;
+  s = (0.5 * b2) * sd * rc;
+  t = s * rc;
+}
 
 // Brent-Luk tournament: data source of position i after one round (n even; pairs are (2k, 2k+1))
 B200_HD constexpr int bl_src(int i, int n) {

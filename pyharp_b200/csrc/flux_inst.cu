@@ -37,7 +37,9 @@ __constant__ QuadTables c_qt;
 #define B200_MIN_BLOCKS 1
 #endif
 #endif
-#if B200_NN <= 2
+#if defined(B200_MAXT)
+#define B200_MAX_THREADS B200_MAXT
+#elif B200_NN <= 2
 #define B200_MAX_THREADS 128
 #else
 #define B200_MAX_THREADS 256
