@@ -241,6 +241,16 @@ B200_HD void ws_prefetch_record(const double* wsl, int lev, long tid) {
 #endif
 }
 
+// Validity of pivots / eigenvalues, accumulated on the integer pipe: a double is a usable pivot (finite, > kTiny)
+// exactly when its high word lies in [hi(kTiny), hi(DBL_MAX)]; anything else -- zero, negative, tiny, Inf, NaN --
+// falls outside after the unsigned shift.  Two integer instructions per pivot instead of a DSETP + selects, and
+// one test per layer.
+struct PivotCheck {
+  unsigned worst = 0u;
+  B200_HD void add(double d) { worst = max(worst, (unsigned)B200_HIWORD(d) - 0x03B8F2B0u); }
+  B200_HD bool bad() const { return worst > 0x7FEFFFFFu - 0x03B8F2B0u; }
+};
+
 // Jacobi rotation that annihilates g_pq (small-angle root): t = tan, s = sin, c = cos of the angle, from the
 // half-angle identities with two reciprocal square roots -- no sqrt, no division (measured cost of the classical
 // form t = b / (d + sign(d) sqrt(d^2 + b^2)), c = 1/sqrt(1 + t^2), tau = s / (1 + c): 49 DFMA-equivalents, this
@@ -275,13 +285,14 @@ B200_HD constexpr int bl_src(int i, int n) {
 #undef B200_UNROLL
 #undef B200_FN
 
-template <int NN, typename QT>
+// NOMOM = the launch carries no phase-function moments (nprop <= 2): isotropic scattering, compile-time lmax = 1
+template <int NN, bool NOMOM = false, typename QT>
 B200_HD void solve_flux_one(const SolveParams& p, const QT& qt, long s, long tid, bool active = true) {
 #ifndef B200_UNROLL_MAX_NN
 #define B200_UNROLL_MAX_NN 4
 #endif
-  if constexpr (NN <= B200_UNROLL_MAX_NN) solve_flux_one_u<NN>(p, qt, s, tid, active);
-  else solve_flux_one_r<NN>(p, qt, s, tid, active);
+  if constexpr (NN <= B200_UNROLL_MAX_NN) solve_flux_one_u<NN, NOMOM>(p, qt, s, tid, active);
+  else solve_flux_one_r<NN, NOMOM>(p, qt, s, tid, active);
 }
 
 }  // namespace b200

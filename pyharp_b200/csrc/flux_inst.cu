@@ -44,6 +44,13 @@ __constant__ QuadTables c_qt;
 #else
 #define B200_MAX_THREADS 256
 #endif
+// NOMOM: instantiation for launches without phase-function moments (nprop <= 2; amars_sw, amars_lw, lbl shapes)
+#if B200_NN <= 4
+#define B200_HAVE_NOMOM 1
+#else
+#define B200_HAVE_NOMOM 0  // large stream counts always come with moments; one (large) kernel is enough
+#endif
+template <bool NOMOM>
 __global__ void __launch_bounds__(B200_MAX_THREADS, B200_MIN_BLOCKS) disort_flux_kernel(SolveParams p) {
   const long nthreads = (long)gridDim.x * blockDim.x;
   const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -53,7 +60,7 @@ __global__ void __launch_bounds__(B200_MAX_THREADS, B200_MIN_BLOCKS) disort_flux
   for (long base = (long)blockIdx.x * blockDim.x; base < nsolve; base += nthreads) {
     const long s = base + threadIdx.x;
     const bool active = s < nsolve;
-    solve_flux_one<B200_NN>(p, c_qt, active ? s : nsolve - 1, tid, active);
+    solve_flux_one<B200_NN, NOMOM>(p, c_qt, active ? s : nsolve - 1, tid, active);
   }
 }
 
@@ -72,14 +79,19 @@ size_t smem_bytes(int block) {
 cudaError_t occupancy(int block, int* blocks_per_sm) {
   const size_t sm = smem_bytes(block);
   if (sm > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(disort_flux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaError_t e = cudaFuncSetAttribute(disort_flux_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return e;
   }
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, disort_flux_kernel, block, sm);
+  // (the no-moments instantiation never needs more registers than the general one)
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, disort_flux_kernel<false>, block, sm);
 }
 
 cudaError_t launch(const SolveParams& p, unsigned grid, int block, cudaStream_t stream) {
-  disort_flux_kernel<<<grid, block, smem_bytes(block), stream>>>(p);
+#if B200_HAVE_NOMOM
+  if (p.nprop <= 2) disort_flux_kernel<true><<<grid, block, smem_bytes(block), stream>>>(p);
+  else
+#endif
+    disort_flux_kernel<false><<<grid, block, smem_bytes(block), stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -20,7 +20,10 @@ static void run(SolveParams& p, const QuadTables& qt) {
   p.ws_threads = 1;
   p.s0 = 0;
   p.nlocal = nsolve;
-  for (long s = 0; s < nsolve; ++s) solve_flux_one<NN>(p, qt, s, 0);
+  for (long s = 0; s < nsolve; ++s) {
+    if (p.nprop <= 2 && NN <= 4) solve_flux_one<NN, true>(p, qt, s, 0);  // same dispatch as flux_inst.cu
+    else solve_flux_one<NN, false>(p, qt, s, 0);
+  }
 }
 
 extern "C" int hostsim_flux(int nwave, int ncol, int nlyr, int nstr, int nprop, unsigned flags,

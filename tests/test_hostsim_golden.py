@@ -168,3 +168,25 @@ def test_conservative_scattering_is_dithered():
     assert G.relerr(got, ld) < 1e-8
     assert G.relerr(f64, ld) < 1e-5
     assert np.isfinite(got).all() and (got >= -1e-12).all()
+
+
+def test_varying_cutoff_depth_across_solves():
+    """Every third solve is cut off part-way down (abstau >= 10, c_disort_set's ncut) while its neighbours are not:
+    the workspace slice and the per-thread state are re-used from solve to solve and must not leak between them."""
+    from pyharp_b200 import workloads as W
+    wl = W.make("amars_sw", nwave=50, ncol=7, nlyr=10)
+    prop = wl.prop.copy()
+    flat = prop.reshape(-1, prop.shape[2], prop.shape[3])
+    rng = np.random.default_rng(7)
+    for k in range(0, flat.shape[0], 3):
+        flat[k, :, 0] = rng.uniform(0.5, 6.0, size=flat.shape[1])
+        flat[k, :, 1] = rng.uniform(0.0, 0.3, size=flat.shape[1])
+    ref, _, st = O.forward(prop, wl.bc, wl.temf, nstr=wl.nstr, flags=wl.flags, wave_lower=wl.wave_lower,
+                           wave_upper=wl.wave_upper)
+    assert not st.any()
+    out = H.flux(prop, wl.bc, wl.temf, nstr=wl.nstr, flags=wl.flags, wave_lower=wl.wave_lower,
+                 wave_upper=wl.wave_upper)
+    flx = out[0] if isinstance(out, tuple) else out
+    assert int((ref[:, :, 0, 1] == 0).sum()) > 50  # the cut-off really happens
+    scale = np.max(np.abs(ref), axis=(2, 3), keepdims=True)
+    assert float(np.max(np.abs(flx - ref) / scale)) < 1e-9
