@@ -300,10 +300,16 @@ def main():
         hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
         fp64_peak = fp64_peak_tflops(local)
         W_, Q_ = wl.flops_per_solve(), wl.bytes_per_solve()
-        traffic = None
-        try:  # DRAM bytes per launch of the solve kernel from the committed ncu --set full capture of this workload
+        traffic, executed = None, None
+        try:  # per-solve counters of the solve kernel from the committed ncu --set full capture of this workload
             tr = json.load(open(os.path.join(ROOT, "profiles", "r01", "traffic.json")))[args.workload]
             traffic = tr["bytes_per_launch"] / tr["solves_per_launch"] * wl.nsolve
+            ex_tf = tr["executed_flop_per_solve"] * wl.nsolve / (kernel_ms * 1e-3) / 1e12
+            executed = {"flop_per_solve": tr["executed_flop_per_solve"], "tflops": ex_tf, "frac_of_fp64_peak": ex_tf / fp64_peak,
+                        "fp64_pipe_active_pct_ncu": tr["fp64_pipe_active_pct"],
+                        "dram_gbs": traffic / (kernel_ms * 1e-3) / 1e9,
+                        "dram_frac_of_hbm_peak": traffic / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
+                        "source": tr.get("capture", "profiles/r01")}
         except Exception:  # noqa: BLE001
             pass
         ach_tf = W_ * wl.nsolve / (kernel_ms * 1e-3) / 1e12
@@ -319,10 +325,13 @@ def main():
                             "frac": ach_tf / fp64_peak, "traffic": traffic,
                             "peak_source": "DFMA-saturating kernel measured in this run (b200disort_fp64_peak); "
                                            "profiles/microbench/fp64_peak_r01.json has the sweep",
+                            "executed": executed,
                             "note": "achieved = reference-algorithm flop count W (SURVEY.md 8d) x solves / kernel time. "
-                                    "The adding-method kernel executes ~1/3 of W (ncu: profiles/r01/ncu_full_*_summary.txt, "
-                                    "FP64 pipe 46 % active on this workload), so frac can exceed 1; traffic = DRAM bytes per "
-                                    "launch from the committed ncu capture (back-sweep workspace dominates)"},
+                                    "The adding-method kernel executes about a third of W, so frac can exceed 1; the "
+                                    "utilisation actually reached is in `executed`: FP64 instructions the kernel issues "
+                                    "(ncu count per solve x this run's rate) against the measured DFMA peak, and its DRAM "
+                                    "traffic (ncu bytes per solve x this run's rate; back-sweep workspace dominates) "
+                                    "against the measured HBM copy bandwidth"},
                "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                                 "frac": ach_gbs / hbm_peak, "peak_source": hbm_src},
                "e2e": e2e}

@@ -208,6 +208,10 @@ B200_HD T& pick_ref(T& a, T& b) {
 }
 
 constexpr int kMaxSweeps = 16;
+// largest nn whose scratch matrices share storage explicitly (disort_solver_body.inc, kShare)
+#ifndef B200_SHARE_MAX_NN
+#define B200_SHARE_MAX_NN 4
+#endif
 #ifndef B200_BS_DEPTH
 #define B200_BS_DEPTH 3
 #endif
@@ -222,7 +226,14 @@ constexpr int kWsLanes = 32;
 #else
 constexpr int kWsLanes = 1;
 #endif
-constexpr int kWsPrefetchAhead = 4;  // levels between a record's L2 prefetch and its register load
+// levels between a record's L2 prefetch and its register load: enough levels that their arithmetic covers an HBM
+// round trip -- a level is ~4 NSAVE instructions, so small records need a longer run-ahead (B200_WS_AHEAD_INSTR
+// instructions' worth)
+#ifndef B200_WS_AHEAD_INSTR
+#define B200_WS_AHEAD_INSTR 400
+#endif
+template <int NSAVE>
+constexpr int kWsPrefetchAhead = (B200_WS_AHEAD_INSTR + 4 * NSAVE - 1) / (4 * NSAVE) < 3 ? 3 : (B200_WS_AHEAD_INSTR + 4 * NSAVE - 1) / (4 * NSAVE);
 
 // Prefetch the (warp, level) record -- NSAVE * kWsLanes doubles, contiguous -- one 128-byte line per lane and
 // instruction.  wsl is the lane's own base pointer (it already includes the lane offset).
@@ -240,6 +251,64 @@ B200_HD void ws_prefetch_record(const double* wsl, int lev, long tid) {
   (void)wsl; (void)lev; (void)tid;
 #endif
 }
+
+// ---------------------------------------------------------------------------
+// TMA-fed back sweep (nstr <= 8).  With the [warp][level][element][lane] layout the record of one (warp, level) is a
+// contiguous, 256-byte aligned run of NSAVE * 256 bytes, i.e. exactly what one 1-D bulk copy moves.  Each warp owns
+// a ring of kStages such records in shared memory; lane 0 issues `cp.async.bulk` for the records several levels
+// ahead, completion is counted by one mbarrier per stage, and the 32 lanes then read their elements with
+// conflict-free LDS.  Why not plain loads into registers: ptxas puts every LDG of the register ring on ONE
+// scoreboard, and a scoreboard can only be waited to zero -- so using the oldest buffer waited for the youngest
+// loads as well, one full HBM latency per level (ncu: 21 % of the amars_lw samples on 2.6 % of its instructions).
+// The mbarrier ring has per-stage completion, and one instruction per warp replaces 25 loads per thread.
+// ---------------------------------------------------------------------------
+#ifndef B200_TMA_BACK
+#define B200_TMA_BACK 1
+#endif
+template <int NSAVE>
+struct TmaRing {
+  // stages: what fits 150-200 KB of shared memory per SM at the kernel's residency (8 warps/SM at nn = 4,
+  // 16 warps/SM below), at most 8
+#ifdef B200_TMA_STAGES
+  static constexpr int kStages = B200_TMA_STAGES;
+#else
+  static constexpr int kStages = NSAVE >= 16 ? 3 : NSAVE >= 9 ? 5 : 8;
+#endif
+  static constexpr int kRecDoubles = NSAVE * kWsLanes;
+  static constexpr int kRecBytes = kRecDoubles * 8;
+  static constexpr int kWarpDoubles = kStages * kRecDoubles + 16;  // + 128 bytes: the stage barriers
+  static constexpr bool kUsed = B200_TMA_BACK && NSAVE <= 32;
+};
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ unsigned b200_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void b200_mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b200_smem_u32(bar)), "r"(count) : "memory");
+}
+// arm the barrier with the byte count of the copy and start the copy (issued by one lane)
+__device__ __forceinline__ void b200_tma_load(double* dst, const double* src, int bytes, unsigned long long* bar) {
+  const unsigned b = b200_smem_u32(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   b200_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(b)
+               : "memory");
+}
+__device__ __forceinline__ void b200_mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned b = b200_smem_u32(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "B200_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra B200_DONE;\n"
+      "bra B200_WAIT;\n"
+      "B200_DONE:\n"
+      "}\n" ::"r"(b),
+      "r"(parity)
+      : "memory");
+}
+#endif
 
 // Validity of pivots / eigenvalues, accumulated on the integer pipe: a double is a usable pivot (finite, > kTiny)
 // exactly when its high word lies in [hi(kTiny), hi(DBL_MAX)]; anything else -- zero, negative, tiny, Inf, NaN --
@@ -287,12 +356,12 @@ B200_HD constexpr int bl_src(int i, int n) {
 
 // NOMOM = the launch carries no phase-function moments (nprop <= 2): isotropic scattering, compile-time lmax = 1
 template <int NN, bool NOMOM = false, typename QT>
-B200_HD void solve_flux_one(const SolveParams& p, const QT& qt, long s, long tid, bool active = true) {
+B200_HD void solve_flux_one(const SolveParams& p, const QT& qt, long s, long tid, bool active, unsigned& ring_pos) {
 #ifndef B200_UNROLL_MAX_NN
 #define B200_UNROLL_MAX_NN 4
 #endif
-  if constexpr (NN <= B200_UNROLL_MAX_NN) solve_flux_one_u<NN, NOMOM>(p, qt, s, tid, active);
-  else solve_flux_one_r<NN, NOMOM>(p, qt, s, tid, active);
+  if constexpr (NN <= B200_UNROLL_MAX_NN) solve_flux_one_u<NN, NOMOM>(p, qt, s, tid, active, ring_pos);
+  else solve_flux_one_r<NN, NOMOM>(p, qt, s, tid, active, ring_pos);
 }
 
 }  // namespace b200

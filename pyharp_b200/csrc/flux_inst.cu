@@ -21,6 +21,7 @@ namespace b200 {
 namespace {
 
 __constant__ QuadTables c_qt;
+constexpr int kNsave = B200_NN * B200_NN + 2 * B200_NN + 1;
 
 // resident CTAs per SM asked of ptxas: the small stream counts are latency / bandwidth bound and want warps
 // (128 registers per thread), the larger ones want every register they can get
@@ -55,12 +56,26 @@ __global__ void __launch_bounds__(B200_MAX_THREADS, B200_MIN_BLOCKS) disort_flux
   const long nthreads = (long)gridDim.x * blockDim.x;
   const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long nsolve = p.nlocal;
+  // position in the warp's ring of back-sweep records (stage = pos % stages, barrier parity = pos / stages)
+  unsigned ring_pos = 0;
+  if constexpr (TmaRing<kNsave>::kUsed) {
+    using Ring = TmaRing<kNsave>;
+    extern __shared__ __align__(128) double b200_smem[];
+    if ((threadIdx.x & 31) == 0) {
+      unsigned long long* bars = reinterpret_cast<unsigned long long*>(
+          b200_smem + (size_t)(threadIdx.x >> 5) * Ring::kWarpDoubles + Ring::kStages * Ring::kRecDoubles);
+      for (int k = 0; k < Ring::kStages; ++k) b200_mbar_init(bars + k, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+  }
   // CTA-uniform trip count: the solver contains CTA barriers (lockstep walk); threads beyond the end of the
   // batch shadow the last solve and write nothing
   for (long base = (long)blockIdx.x * blockDim.x; base < nsolve; base += nthreads) {
     const long s = base + threadIdx.x;
     const bool active = s < nsolve;
-    solve_flux_one<B200_NN, NOMOM>(p, c_qt, active ? s : nsolve - 1, tid, active);
+    solve_flux_one<B200_NN, NOMOM>(p, c_qt, active ? s : nsolve - 1, tid, active, ring_pos);
   }
 }
 
@@ -68,6 +83,7 @@ cudaError_t upload_tables(const QuadTables* qt) { return cudaMemcpyToSymbol(c_qt
 
 // dynamic shared memory per CTA: the parked stack state (Ra packed symmetric + da) of every thread
 size_t smem_bytes(int block) {
+  if (TmaRing<kNsave>::kUsed) return (size_t)(block / 32) * TmaRing<kNsave>::kWarpDoubles * sizeof(double);
 #if B200_SMEM_STACK
   return (size_t)(B200_NN * (B200_NN + 1) / 2 + B200_NN) * block * sizeof(double);
 #else
@@ -81,6 +97,10 @@ cudaError_t occupancy(int block, int* blocks_per_sm) {
   if (sm > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(disort_flux_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return e;
+#if B200_HAVE_NOMOM
+    e = cudaFuncSetAttribute(disort_flux_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return e;
+#endif
   }
   // (the no-moments instantiation never needs more registers than the general one)
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, disort_flux_kernel<false>, block, sm);

@@ -20,9 +20,10 @@ static void run(SolveParams& p, const QuadTables& qt) {
   p.ws_threads = 1;
   p.s0 = 0;
   p.nlocal = nsolve;
+  unsigned ring_pos = 0;  // (device only: position in the warp's shared-memory ring of back-sweep records)
   for (long s = 0; s < nsolve; ++s) {
-    if (p.nprop <= 2 && NN <= 4) solve_flux_one<NN, true>(p, qt, s, 0);  // same dispatch as flux_inst.cu
-    else solve_flux_one<NN, false>(p, qt, s, 0);
+    if (p.nprop <= 2 && NN <= 4) solve_flux_one<NN, true>(p, qt, s, 0, true, ring_pos);  // same dispatch as flux_inst.cu
+    else solve_flux_one<NN, false>(p, qt, s, 0, true, ring_pos);
   }
 }
 
