@@ -324,6 +324,8 @@ extern "C" void b200disort_destroy(b200disort_handle* h) {
   delete h;
 }
 
+constexpr long kHostChunkDiv = 1;  // host-path chunk = resident wave / kHostChunkDiv
+
 // grow-only device buffer
 static int ensure_dev(double** ptr, size_t* have, size_t need) {
   if (need <= *have) return B200DISORT_OK;
@@ -352,11 +354,13 @@ static int launch_flux(b200disort_handle* h, SolveParams& p, cudaStream_t stream
   }
   long grid = std::min<long>((p.nlocal + block - 1) / block, (long)h->sm_count * h->occ);
   const long nthreads = grid * block;
-  const size_t need = (size_t)p.nlyr * inst->nsave * nthreads * sizeof(double);
+  const size_t half = (size_t)p.nlyr * inst->nsave * nthreads;
+  const size_t need = half * inst->ws_halves * sizeof(double);
   int rc = ensure_dev(ws, ws_bytes, need);
   if (rc != B200DISORT_OK) return rc;
   p.ws = *ws;
   p.ws_threads = nthreads;
+  p.ws_half = (long)half;
   if (timed) {
     if (h->ring_used == b200disort_handle::kRing) {  // fold the ring (blocks until those solves finished)
       CU_TRY(cudaEventSynchronize(h->evB[h->ring_used - 1]));
@@ -603,7 +607,13 @@ extern "C" int b200disort_solve_host(b200disort_handle* h, const double* prop, i
     h->occ = occ < 1 ? 1 : occ;
   }
   const long wave = (long)h->sm_count * h->occ * 128;  // (launch_flux may be told another CTA size by the tuning knobs)
-  const long chunk = std::min(nsolve, wave);
+  // The host path is bound by PCIe, not by the kernels (amars_lw: 0.9 ms of copies against 0.3 ms of solve per
+  // wave), so its chunks are a fraction of a wave: the first H2D and the last D2H of a call, which nothing
+  // overlaps, shrink with the chunk.  B200DISORT_HOST_CHUNK_DIV overrides the divisor (profiling knob).
+  static const int env_div = std::getenv("B200DISORT_HOST_CHUNK_DIV") ? std::atoi(std::getenv("B200DISORT_HOST_CHUNK_DIV")) : 0;
+  const long div = env_div > 0 ? env_div : kHostChunkDiv;
+  const long part = std::max<long>(128 * 16, ((wave / div + 127) / 128) * 128);
+  const long chunk = std::min(nsolve, part);
   const long nchunk = (nsolve + chunk - 1) / chunk;
   const size_t in_per = (size_t)c.nlyr * nprop + n_bc;  // doubles per solve
   const size_t out_per = (size_t)nlev * 2;

@@ -129,7 +129,8 @@ struct SolveParams {
   int32_t* status; // (nwave,ncol)
   long s0;         // batch index of this launch's first solve (chunked host path); prop/bc/flx/status are chunk-local
   long nlocal;     // solves in this launch
-  double* ws;      // back-sweep workspace: [warp][level][elem][lane] (kWsLanes lanes per group)
+  double* ws;      // back-sweep workspace: [half][warp][level][elem][lane] (kWsLanes lanes per group)
+  long ws_half;    // doubles per half (carried back sweep: two halves; otherwise unused)
   long ws_threads; // threads the workspace was sized for (a multiple of kWsLanes)
 };
 
@@ -310,6 +311,44 @@ __device__ __forceinline__ void b200_mbar_wait(unsigned long long* bar, unsigned
 }
 #endif
 
+// ---------------------------------------------------------------------------
+// Carried back sweep (nstr <= 8): the back sweep of a finished forward sweep rides on the same thread's NEXT
+// solve -- one level is emitted at the end of every layer of the next forward sweep, its record copied into the
+// warp's ring by TMA at least one layer (~2000 instructions) earlier, so no warp ever waits for HBM between
+// two forward sweeps.  Forward sweep alone: 3.85 ms per amars_lw launch; with a stand-alone back sweep: 4.50 ms;
+// carried: 4.38 ms (profiles/r01, sweeps e11, e12) -- what remains is the ~100 instructions a level costs at the
+// per-warp issue rate of this kernel, not memory latency.  The two solves use alternating halves of the workspace.  Everything that
+// synchronises (mbarrier waits, __syncwarp, the refill by lane 0) is warp-uniform: `lev` is the same in all lanes
+// (lanes whose medium is cut off higher up skip levels they do not own), and the layer loop of a warp runs until
+// all of its lanes are cut off.
+// ---------------------------------------------------------------------------
+#ifndef B200_CARRY_BACK
+#define B200_CARRY_BACK 1
+#endif
+// Measured (profiles/r01, sweep e12): +3 % at nstr = 8 (amars_lw), none on amars_sw, -2.4 % at nstr = 4 (LBL, where a
+// layer of the forward sweep is too short to amortise the per-level bookkeeping) -- so it is used from nn = 4 up.
+template <int NN>
+constexpr bool kCarryBack = B200_CARRY_BACK && NN >= 4 && TmaRing<NN * NN + 2 * NN + 1>::kUsed;
+
+template <int NN>
+struct BackPend {
+  double up[NN];           // upward radiation at level lev + 1
+  double* out = nullptr;   // flux rows of the pending solve
+  const double* wsl = nullptr;  // lane base (level 0) of its workspace half
+  int ncut = 0;            // this lane emits levels lev < ncut
+  int lev = -1;            // warp-uniform: next level to emit, counting down; < 0: nothing pending
+  int nlyr = 0;
+  bool bad = false, active = false;
+};
+
+#if defined(__CUDA_ARCH__)
+#define B200_WARP_ANY(pred) (__any_sync(0xffffffffu, (pred)) != 0)
+#define B200_WARP_SYNC() __syncwarp()
+#else
+#define B200_WARP_ANY(pred) (pred)
+#define B200_WARP_SYNC() ((void)0)
+#endif
+
 // Validity of pivots / eigenvalues, accumulated on the integer pipe: a double is a usable pivot (finite, > kTiny)
 // exactly when its high word lies in [hi(kTiny), hi(DBL_MAX)]; anything else -- zero, negative, tiny, Inf, NaN --
 // falls outside after the unsigned shift.  Two integer instructions per pivot instead of a DSETP + selects, and
@@ -356,12 +395,23 @@ B200_HD constexpr int bl_src(int i, int n) {
 
 // NOMOM = the launch carries no phase-function moments (nprop <= 2): isotropic scattering, compile-time lmax = 1
 template <int NN, bool NOMOM = false, typename QT>
-B200_HD void solve_flux_one(const SolveParams& p, const QT& qt, long s, long tid, bool active, unsigned& ring_pos) {
+B200_HD void solve_flux_one(const SolveParams& p, const QT& qt, long s, long tid, bool active, unsigned& ring_pos,
+                            BackPend<NN>& pend, int wshalf) {
 #ifndef B200_UNROLL_MAX_NN
 #define B200_UNROLL_MAX_NN 4
 #endif
-  if constexpr (NN <= B200_UNROLL_MAX_NN) solve_flux_one_u<NN, NOMOM>(p, qt, s, tid, active, ring_pos);
-  else solve_flux_one_r<NN, NOMOM>(p, qt, s, tid, active, ring_pos);
+  if constexpr (NN <= B200_UNROLL_MAX_NN) solve_flux_one_u<NN, NOMOM>(p, qt, s, tid, active, ring_pos, pend, wshalf);
+  else solve_flux_one_r<NN, NOMOM>(p, qt, s, tid, active, ring_pos, pend, wshalf);
+}
+
+// finishes a pending (carried) back sweep after a thread's last solve
+template <int NN, typename QT>
+B200_HD void drain_back_sweep(BackPend<NN>& pend, const QT& qt, long tid, unsigned& ring_pos) {
+  if constexpr (NN <= B200_UNROLL_MAX_NN) {
+    while (pend.lev >= 0) back_level_u<NN>(pend, qt, tid, ring_pos);
+  } else {
+    while (pend.lev >= 0) back_level_r<NN>(pend, qt, tid, ring_pos);
+  }
 }
 
 }  // namespace b200

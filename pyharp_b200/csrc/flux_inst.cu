@@ -72,10 +72,16 @@ __global__ void __launch_bounds__(B200_MAX_THREADS, B200_MIN_BLOCKS) disort_flux
   }
   // CTA-uniform trip count: the solver contains CTA barriers (lockstep walk); threads beyond the end of the
   // batch shadow the last solve and write nothing
-  for (long base = (long)blockIdx.x * blockDim.x; base < nsolve; base += nthreads) {
+  BackPend<B200_NN> pend;  // carried back sweep of the previous solve (nstr <= 8)
+  int it = 0;
+  for (long base = (long)blockIdx.x * blockDim.x; base < nsolve; base += nthreads, ++it) {
     const long s = base + threadIdx.x;
     const bool active = s < nsolve;
-    solve_flux_one<B200_NN, NOMOM>(p, c_qt, active ? s : nsolve - 1, tid, active, ring_pos);
+    solve_flux_one<B200_NN, NOMOM>(p, c_qt, active ? s : nsolve - 1, tid, active, ring_pos, pend, it & 1);
+  }
+  if constexpr (kCarryBack<B200_NN>) {
+    __syncwarp();
+    drain_back_sweep<B200_NN>(pend, c_qt, tid, ring_pos);
   }
 }
 
@@ -115,7 +121,7 @@ cudaError_t launch(const SolveParams& p, unsigned grid, int block, cudaStream_t 
   return cudaGetLastError();
 }
 
-const FluxInst kInst = {B200_NN, B200_NN * B200_NN + 2 * B200_NN + 1, B200_MAX_THREADS, upload_tables, occupancy, launch};
+const FluxInst kInst = {B200_NN, B200_NN * B200_NN + 2 * B200_NN + 1, B200_MAX_THREADS, kCarryBack<B200_NN> ? 2 : 1, upload_tables, occupancy, launch};
 
 }  // namespace
 

@@ -12,6 +12,7 @@ struct FluxInst {
   int nn;
   int nsave;  // doubles stored per level and solve for the back sweep
   int max_threads;  // __launch_bounds__ of the kernel
+  int ws_halves;    // 2 when the back sweep is carried into the thread's next solve (alternating workspace halves)
   cudaError_t (*upload_tables)(const QuadTables*);
   cudaError_t (*occupancy)(int block, int* blocks_per_sm);
   cudaError_t (*launch)(const SolveParams&, unsigned grid, int block, cudaStream_t);

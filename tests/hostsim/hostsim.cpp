@@ -15,16 +15,23 @@ template <int NN>
 static void run(SolveParams& p, const QuadTables& qt) {
   const long nsolve = (long)p.nwave * p.ncol;
   constexpr int NSAVE = NN * NN + 2 * NN + 1;
-  std::vector<double> ws((size_t)p.nlyr * NSAVE);
+  // same driver structure as disort_flux_kernel (flux_inst.cu): where the kernel carries the back sweep of one
+  // solve into the thread's next solve, so does this loop (alternating workspace halves, drain at the end)
+  const size_t half = (size_t)p.nlyr * NSAVE;
+  std::vector<double> ws(2 * half);
   p.ws = ws.data();
   p.ws_threads = 1;
+  p.ws_half = (long)half;
   p.s0 = 0;
   p.nlocal = nsolve;
   unsigned ring_pos = 0;  // (device only: position in the warp's shared-memory ring of back-sweep records)
-  for (long s = 0; s < nsolve; ++s) {
-    if (p.nprop <= 2 && NN <= 4) solve_flux_one<NN, true>(p, qt, s, 0, true, ring_pos);  // same dispatch as flux_inst.cu
-    else solve_flux_one<NN, false>(p, qt, s, 0, true, ring_pos);
+  BackPend<NN> pend;
+  int it = 0;
+  for (long s = 0; s < nsolve; ++s, ++it) {
+    if (p.nprop <= 2 && NN <= 4) solve_flux_one<NN, true>(p, qt, s, 0, true, ring_pos, pend, it & 1);  // same dispatch as flux_inst.cu
+    else solve_flux_one<NN, false>(p, qt, s, 0, true, ring_pos, pend, it & 1);
   }
+  if constexpr (kCarryBack<NN>) drain_back_sweep<NN>(pend, qt, 0, ring_pos);
 }
 
 extern "C" int hostsim_flux(int nwave, int ncol, int nlyr, int nstr, int nprop, unsigned flags,
