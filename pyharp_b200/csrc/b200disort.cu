@@ -608,8 +608,9 @@ extern "C" int b200disort_solve_host(b200disort_handle* h, const double* prop, i
   }
   const long wave = (long)h->sm_count * h->occ * 128;  // (launch_flux may be told another CTA size by the tuning knobs)
   // The host path is bound by PCIe, not by the kernels (amars_lw: 0.9 ms of copies against 0.3 ms of solve per
-  // wave), so its chunks are a fraction of a wave: the first H2D and the last D2H of a call, which nothing
-  // overlaps, shrink with the chunk.  B200DISORT_HOST_CHUNK_DIV overrides the divisor (profiling knob).
+  // wave).  Smaller chunks would shrink the first H2D and the last D2H of a call, which nothing overlaps;
+  // measured (profiles/r01, sweep e13): +2 % at half a wave on amars_lw, losses elsewhere and below a quarter
+  // wave, so the chunk stays one wave.  B200DISORT_HOST_CHUNK_DIV overrides the divisor (profiling knob).
   static const int env_div = std::getenv("B200DISORT_HOST_CHUNK_DIV") ? std::atoi(std::getenv("B200DISORT_HOST_CHUNK_DIV")) : 0;
   const long div = env_div > 0 ? env_div : kHostChunkDiv;
   const long part = std::max<long>(128 * 16, ((wave / div + 127) / 128) * 128);
