@@ -14,6 +14,7 @@
  *   b200_rfm_optics      <- RFMImpl::forward + get_reftemp (src/opacity/rfm.cpp:122-197)
  *   b200_layer2level     <- harp::layer2level (src/utils/layer2level.cpp:7-79)
  *   b200_spherical_flux_correction <- harp::spherical_flux_correction (src/utils/spherical_flux_correction.cpp:3-18)
+ *   b200_heating_rate <- the heating-rate post-processing of examples/amars_sw.cpp:290-301
  *   b200_band_optics     <- the optical-property mixing the examples do before the solve
  *                           (examples/amars_sw.cpp:262-273; RadiationBandImpl::forward
  *                           src/radiation/radiation_band.cpp:83-116 in the 4-D layout)
@@ -68,6 +69,13 @@ int b200_band_optics(const double* const* att, const int* nprops, int natt, cons
  * uses the already corrected flux of level i+1. */
 int b200_spherical_flux_correction(double* flx, const double* x1f, const double* area, const double* vol, long nrow,
                                    int nx1, void* stream);
+
+/* Heating rate per layer from band-integrated fluxes, the post-processing of examples/amars_sw.cpp:290-301:
+ * bflx (ncol, nlyr+1, 2) = (up, down) with level 0 at the surface (the output of b200disort_reduce_band, i.e. the
+ * example's integrate_result, examples/amars_sw.cpp:173-196), rho / dz (ncol, nlyr) layer density [kg/m^3] and
+ * thickness [m], cp [J/(kg K)]; dTdt (ncol, nlyr) [K/s] = -(1 / (rho cp)) (net[k+1] - net[k]) / dz, net = up - down. */
+int b200_heating_rate(const double* bflx, const double* rho, const double* dz, double cp, long ncol, int nlyr,
+                      double* dTdt, void* stream);
 
 #ifdef __cplusplus
 }

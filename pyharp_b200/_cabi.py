@@ -39,7 +39,7 @@ EXPORTS = ("b200disort_create", "b200disort_solve", "b200disort_solve_host",
            "b200disort_get_stats", "b200disort_fp64_peak", "b200disort_destroy",
            "b200disort_strerror", "b200disort_version")
 OPACITY_EXPORTS = ("b200_interpn", "b200_aerosol_optics", "b200_rfm_optics", "b200_layer2level", "b200_band_optics",
-                   "b200_spherical_flux_correction")
+                   "b200_spherical_flux_correction", "b200_heating_rate")
 
 _lib = None
 
@@ -88,6 +88,8 @@ def lib():
     L.b200_layer2level.argtypes = [vp, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     L.b200_spherical_flux_correction.restype = C.c_int
     L.b200_spherical_flux_correction.argtypes = [vp, vp, vp, vp, C.c_long, C.c_int, vp]
+    L.b200_heating_rate.restype = C.c_int
+    L.b200_heating_rate.argtypes = [vp, vp, vp, C.c_double, C.c_long, C.c_int, vp, vp]
     L.b200_band_optics.restype = C.c_int
     L.b200_band_optics.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                    vp, vp]

@@ -270,6 +270,27 @@ extern "C" int b200_band_optics(const double* const* att, const int* nprops, int
   return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 
+// heating rate of layer k from the band-integrated fluxes (examples/amars_sw.cpp:290-301): net = up - down at the
+// two interfaces, dT/dt = -(1 / (rho cp)) (net[k+1] - net[k]) / dz; same evaluation order as the example
+__global__ void heating_rate_kernel(const double* __restrict__ bflx, const double* __restrict__ rho,
+                                    const double* __restrict__ dz, double cp, long ncol, int nlyr, double* __restrict__ out) {
+  const long n = ncol * nlyr;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const long j = i / nlyr;
+    const int k = (int)(i - j * nlyr);
+    const double* f = bflx + (j * (nlyr + 1) + k) * 2;
+    const double df = f[0] - f[1], df1 = f[2] - f[3];
+    out[i] = -(1.0 / (rho[i] * cp)) * (df1 - df) / dz[i];
+  }
+}
+
+extern "C" int b200_heating_rate(const double* bflx, const double* rho, const double* dz, double cp, long ncol, int nlyr,
+                                 double* dTdt, void* stream) {
+  if (!bflx || !rho || !dz || !dTdt || ncol < 1 || nlyr < 1 || !(cp > 0.0)) return 1;
+  heating_rate_kernel<<<grid_for(ncol * nlyr, 256), 256, 0, (cudaStream_t)stream>>>(bflx, rho, dz, cp, ncol, nlyr, dTdt);
+  return cudaGetLastError() == cudaSuccess ? 0 : 2;
+}
+
 extern "C" int b200_spherical_flux_correction(double* flx, const double* x1f, const double* area, const double* vol, long nrow,
                                               int nx1, void* stream) {
   if (!flx || !x1f || !area || !vol || nrow < 1 || nx1 < 2) return 1;

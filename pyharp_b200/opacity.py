@@ -231,3 +231,26 @@ def spherical_flux_correction(flx, x1f, area, vol):
                                                         flx.numel() // nx1, nx1, _stream())
     _check(rc, "b200_spherical_flux_correction")
     return flx
+
+
+def heating_rate(bflx, rho, dz, cp):
+    """Heating rate [K/s] per layer from band-integrated fluxes on the GPU, the post-processing of
+    examples/amars_sw.cpp:290-301: bflx (..., nlyr+1, 2) = (up, down), level 0 at the surface; rho, dz (..., nlyr).
+    dT/dt[k] = -(1 / (rho[k] cp)) (net[k+1] - net[k]) / dz[k] with net = up - down."""
+    if not (bflx.is_cuda and bflx.dtype == torch.float64):
+        raise RuntimeError("heating_rate: float64 CUDA tensor required (no CPU fallback)")
+    bflx = bflx.contiguous()
+    nlyr = bflx.shape[-2] - 1
+    if bflx.shape[-1] != 2 or nlyr < 1:
+        raise ValueError("bflx must be (..., nlyr+1, 2)")
+    dev = bflx.device
+    lead = bflx.shape[:-2]
+    rho = _dev(rho, dev).expand(*lead, nlyr).contiguous()
+    dz = _dev(dz, dev).expand(*lead, nlyr).contiguous()
+    out = torch.empty(*lead, nlyr, dtype=torch.float64, device=dev)
+    ncol = out.numel() // nlyr
+    with torch.cuda.device(dev):
+        rc = _cabi.lib().b200_heating_rate(bflx.data_ptr(), rho.data_ptr(), dz.data_ptr(), float(cp), ncol, nlyr,
+                                           out.data_ptr(), _stream())
+    _check(rc, "b200_heating_rate")
+    return out

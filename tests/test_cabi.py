@@ -25,7 +25,7 @@ def test_header_symbols_exported():
         assert hasattr(lib, n), f"{n} declared in include/b200disort.h but not exported"
     assert sorted(_cabi.EXPORTS) == names
     onames = declared_functions("b200opacity.h", "b200_")
-    assert len(onames) == 6 and sorted(_cabi.OPACITY_EXPORTS) == onames
+    assert len(onames) == 7 and sorted(_cabi.OPACITY_EXPORTS) == onames
     for n in onames:
         assert hasattr(lib, n), f"{n} declared in include/b200opacity.h but not exported"
 

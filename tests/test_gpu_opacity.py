@@ -103,3 +103,32 @@ def test_spherical_flux_correction_bit_exact(cuda_device):
     flx = torch.from_numpy(z["flx"]).to(cuda_device).contiguous()
     got = OP.spherical_flux_correction(flx, z["x1f"], z["area"], z["vol"]).cpu().numpy()
     assert np.array_equal(got, z["out"])
+
+
+def test_heating_rate_matches_example_arithmetic(cuda_device):
+    """examples/amars_sw.cpp:290-301 restated in numpy with the example's evaluation order: bit-exact.  The fluxes are
+    the band integral (examples/amars_sw.cpp:173-196 = reduce_band with weight d_lambda) of the real amars_sw run."""
+    z = _load("amars_sw_real.npz")
+    flx = torch.from_numpy(z["flx_oracle_ld"]).to(cuda_device)           # (nwave, 1, nlyr+1, 2)
+    d_lambda = 96.19238476953907
+    bflx = (flx * d_lambda).sum(0)                                         # (1, nlyr+1, 2)
+    nlyr = bflx.shape[-2] - 1
+    rng = np.random.default_rng(3)
+    rho = rng.uniform(1e-3, 1.5, size=(1, nlyr))
+    dz = rng.uniform(200.0, 900.0, size=(1, nlyr))
+    cp = 844.0
+    got = OP.heating_rate(bflx, rho, dz, cp).cpu().numpy()
+    b = bflx.cpu().numpy()
+    want = np.empty((1, nlyr))
+    for k in range(nlyr):
+        df = b[0, k, 0] - b[0, k, 1]
+        df1 = b[0, k + 1, 0] - b[0, k + 1, 1]
+        want[0, k] = -(1 / (rho[0, k] * cp)) * (df1 - df) / dz[0, k]
+    assert np.array_equal(got, want)
+    # many columns at once
+    bf = torch.from_numpy(rng.uniform(0, 500, size=(7, 5, nlyr + 1, 2))).to(cuda_device)
+    r2, d2 = rng.uniform(0.01, 1.0, size=(7, 5, nlyr)), rng.uniform(100, 1000, size=(7, 5, nlyr))
+    g2 = OP.heating_rate(bf, r2, d2, cp).cpu().numpy()
+    bn = bf.cpu().numpy()
+    net = bn[..., 0] - bn[..., 1]
+    assert np.array_equal(g2, -(1 / (r2 * cp)) * (net[..., 1:] - net[..., :-1]) / d2)
