@@ -64,8 +64,11 @@ extern "C" int hostsim_flux(int nwave, int ncol, int nlyr, int nstr, int nprop, 
   switch (nstr) {
     case 2: run<1>(p, qt); break;
     case 4: run<2>(p, qt); break;
+    case 6: run<3>(p, qt); break;
     case 8: run<4>(p, qt); break;
+    case 12: run<6>(p, qt); break;
     case 16: run<8>(p, qt); break;
+    case 24: run<12>(p, qt); break;
     case 32: run<16>(p, qt); break;
     default: return 1;
   }
