@@ -1,0 +1,20 @@
+"""Two-GPU run of tests/nccl_band_flux.py (the multi-GPU row of SURVEY.md 8e with the real CUDA path and NCCL);
+skipped on boxes with a single GPU, where tests/test_multirank_gloo.py covers the host logic."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_band_flux_nccl():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", os.path.join(HERE, "nccl_band_flux.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "NCCL_BAND_FLUX_OK" in r.stdout

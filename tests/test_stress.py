@@ -6,8 +6,8 @@ Planck slope across thin layers, near-conservative thick layers), so the bar is
     |kernel - oracle| <= 1e-9 + 2 |oracle - oracle80|        (relative to the largest flux of the solve)
 
 with oracle80 the 80-bit build of the same oracle: the kernel may differ from the reference by no more than the
-reference differs from its own extended-precision evaluation.  The kernel is also required to be within 5e-8 of
-oracle80 outright (it is typically 10x closer to it than the double-precision oracle)."""
+reference differs from its own extended-precision evaluation, and the same bound is asked of |kernel - oracle80|
+(the kernel is typically 10x closer to the 80-bit result than the double-precision oracle is)."""
 import numpy as np
 import pytest
 
@@ -33,7 +33,7 @@ def _bar(c, flx):
     noise = err(ref, r80)
     assert np.all(np.isfinite(flx))
     assert np.all(err(flx, ref) <= 1e-9 + 2.0 * noise), float((err(flx, ref) - 2.0 * noise).max())
-    assert float(err(flx, r80).max()) < 5e-8
+    assert np.all(err(flx, r80) <= 1e-9 + 2.0 * noise), float((err(flx, r80) - 2.0 * noise).max())
 
 
 @pytest.mark.parametrize("nstr", [2, 4, 6, 8, 12, 16, 24, 32])
