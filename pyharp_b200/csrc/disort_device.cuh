@@ -81,13 +81,25 @@ __device__ __forceinline__ double b200_fast_rsqrt(double x) {
 #if defined(B200_LOCKSTEP) && B200_LOCKSTEP
 #define B200_BLOCK_SYNC() __syncthreads()
 #define B200_BLOCK_ANY(pred) (__syncthreads_or(pred) != 0)
+// Jacobi convergence vote in the lockstep build: per warp (B200_JACOBI_WARP_VOTE, the sweep body is small enough to
+// stay in the instruction cache; the CTA re-aligns at the next layer) or per CTA
+#ifndef B200_JACOBI_WARP_VOTE
+#define B200_JACOBI_WARP_VOTE 1
+#endif
+#if B200_JACOBI_WARP_VOTE
+#define B200_JACOBI_ANY(pred) (__any_sync(0xffffffffu, (pred)) != 0)
 #else
-#define B200_BLOCK_SYNC() ((void)0)
-#define B200_BLOCK_ANY(pred) (pred)
+#define B200_JACOBI_ANY(pred) B200_BLOCK_ANY(pred)
 #endif
 #else
 #define B200_BLOCK_SYNC() ((void)0)
 #define B200_BLOCK_ANY(pred) (pred)
+#define B200_JACOBI_ANY(pred) (pred)
+#endif
+#else
+#define B200_BLOCK_SYNC() ((void)0)
+#define B200_BLOCK_ANY(pred) (pred)
+#define B200_JACOBI_ANY(pred) (pred)
 #define B200_PREFETCH(ptr) ((void)0)
 #define B200_RCP(x) (1.0 / (x))
 #define B200_RSQRT(x) (1.0 / sqrt(x))

@@ -289,6 +289,10 @@ class Disort:
             raise RuntimeError(f"b200disort_solve failed: {_cabi.strerror(rc)}")
 
     def get_rad(self, options=None):
+        """Intensities of the last forward(), shape (nwave, ncol, nphi, ntau, numu): cdisort's `uu` memory order
+        (numu fastest) behind the (wave, column) batch axes.  pyharp only prints this tensor
+        (tests/test_disort.cpp:52), so the reference does not pin the axis order; SURVEY.md 8 row a4 records it as
+        inferred from cdisort's layout, and include/b200disort.h documents the same order for the C ABI."""
         if self._rad is None:
             raise RuntimeError("get_rad: no intensities available (onlyfl set or forward not called)")
         return self._rad
