@@ -74,7 +74,8 @@ typedef struct b200disort_handle b200disort_handle;
 
 typedef struct {
   int nwave, ncol, nlyr; /* batch shape: nwave x ncol independent solves */
-  int nstr, nmom;        /* streams (even, 2..64) and phase moments (>= nstr) */
+  int nstr, nmom;        /* streams (even, 2..32; the flux kernel is instantiated for 2,4,6,8,12,16,24,32, other
+                            counts run on the general kernel) and phase moments (>= nstr) */
   int ntau, numu, nphi;  /* user grid sizes (used with USRTAU / USRANG) */
   unsigned flags;        /* B200DISORT_* bitmask */
   double accur;          /* azimuth-series convergence criterion */

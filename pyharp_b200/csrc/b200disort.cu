@@ -203,8 +203,10 @@ extern "C" int b200disort_create(const b200disort_config* cfg, b200disort_handle
   if (cfg->nwave < 1 || cfg->ncol < 1 || cfg->nlyr < 1) return B200DISORT_ERR_INVALID;
   if (cfg->nstr < 2 || (cfg->nstr & 1) || cfg->nmom < cfg->nstr) return B200DISORT_ERR_INVALID;
   if (!(cfg->flags & B200DISORT_LAMBER)) return B200DISORT_ERR_UNSUPPORTED;  // BRDF not on pyharp's path
+  // K1 (the flux kernel) is instantiated for nstr in {2,4,6,8,12,16,24,32}; any other even nstr <= 32 is served by
+  // the general kernel K3, whose sizes are run-time (one CTA per solve: correct, not tuned for throughput)
   const FluxInst* inst = inst_of(cfg->nstr);
-  if (!inst) return B200DISORT_ERR_UNSUPPORTED;  /* nstr in {2,4,6,8,12,16,24,32} */
+  if (!inst && cfg->nstr > 2 * kMaxNN) return B200DISORT_ERR_UNSUPPORTED;
   if ((cfg->flags & B200DISORT_USRTAU) && (cfg->ntau < 1 || !cfg->user_tau)) return B200DISORT_ERR_INVALID;
   const bool onlyfl = cfg->flags & B200DISORT_ONLYFL;
   if (!onlyfl && (cfg->flags & B200DISORT_USRANG) && (cfg->numu < 1 || !cfg->user_mu)) return B200DISORT_ERR_INVALID;
@@ -242,7 +244,7 @@ extern "C" int b200disort_create(const b200disort_config* cfg, b200disort_handle
   // constant tables for this stream count
   QuadTables qt;
   build_quad_tables(cfg->nstr, &qt);
-  CU_TRY(inst->upload_tables(&qt));
+  if (inst) CU_TRY(inst->upload_tables(&qt));
 
   // spectral bands: unique (wvnmlo, wvnmhi) pairs
   if (!h->wave_lower.empty()) {
@@ -461,7 +463,7 @@ extern "C" int b200disort_solve(b200disort_handle* h, const double* prop, int np
   CU_TRY(cudaSetDevice(c.device));
   h->stats.kernel_launches = 0;
   CU_TRY(cudaEventRecord(h->ev0, h->stream));
-  if (!onlyfl || (c.flags & B200DISORT_USRTAU)) return solve_general(h, prop, nprop, bc, temf, flx, uu, status);
+  if (!onlyfl || (c.flags & B200DISORT_USRTAU) || !h->inst) return solve_general(h, prop, nprop, bc, temf, flx, uu, status);
 
   SolveParams p{};
   p.nwave = c.nwave; p.ncol = c.ncol; p.nlyr = c.nlyr; p.nprop = nprop; p.nstr = c.nstr;
@@ -549,7 +551,7 @@ extern "C" int b200disort_solve_host(b200disort_handle* h, const double* prop, i
   CU_TRY(cudaSetDevice(c.device));
   h->stats.kernel_launches = 0;
   using Slot = b200disort_handle::Slot;
-  if (!onlyfl || (c.flags & B200DISORT_USRTAU)) {
+  if (!onlyfl || (c.flags & B200DISORT_USRTAU) || !h->inst) {
     // cold path (test_disort-sized batches): stage everything, one launch, copy back
     const size_t ns = (size_t)c.nwave * c.ncol;
     const double* src[9] = {bc ? bc->umu0 : nullptr, bc ? bc->fbeam : nullptr, bc ? bc->albedo : nullptr,

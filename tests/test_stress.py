@@ -87,3 +87,30 @@ def test_gpu_stress(cuda_device, nstr):
         flx = ds.forward(t(c["prop"]), {k: t(v) for k, v in c["bc"].items()}, t(c["temf"])).cpu().numpy()
         assert int(ds.status().abs().sum()) == 0
         _bar(c, flx)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nstr", [10, 14, 20, 30])
+def test_gpu_stream_counts_without_a_flux_instantiation(cuda_device, nstr):
+    """The flux kernel is compiled for nstr in {2,4,6,8,12,16,24,32}; any other even nstr <= 32 is served by the
+    general kernel (run-time sizes, one CTA per solve) through the same Disort.forward call."""
+    import torch
+    from pyharp_b200 import Disort, DisortOptions
+    c = S.make(nstr, 1, nwave=2, ncol=9, nlyr=11, thermal=True, beam=True)
+    # (moderate inputs: the general kernel follows cdisort's own formulation, so in the extreme regime its rounding
+    # noise is the reference's, not a fraction of it as for the flux kernel)
+    c["prop"][..., 0] = np.clip(c["prop"][..., 0], 1e-4, 10.0)
+    c["prop"][..., 1] = np.clip(c["prop"][..., 1], 0.0, 0.999)
+    op = DisortOptions().flags(c["flags"]).nwave(2).ncol(9)
+    op.ds().nlyr, op.ds().nstr, op.ds().nmom = 11, nstr, nstr
+    op.wave_lower(list(c["wave_lower"])).wave_upper(list(c["wave_upper"]))
+    ds = Disort(op)
+    for dev in (cuda_device, "cpu"):   # device tensors, and the host-pointer entry
+        t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        flx = ds.forward(t(c["prop"]), {k: t(v) for k, v in c["bc"].items()}, t(c["temf"])).cpu().numpy()
+        assert int(ds.status().abs().sum()) == 0
+        ref, _, st = O.forward(c["prop"], c["bc"], c["temf"], nstr=nstr, flags=_bits(c["flags"]),
+                               wave_lower=c["wave_lower"], wave_upper=c["wave_upper"], nthreads=8)
+        assert not st.any()
+        scale = np.max(np.abs(ref), axis=(2, 3), keepdims=True)
+        assert float(np.max(np.abs(flx - ref) / scale)) < 1e-9
