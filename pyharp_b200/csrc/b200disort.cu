@@ -206,6 +206,7 @@ extern "C" int b200disort_create(const b200disort_config* cfg, b200disort_handle
   // K1 (the flux kernel) is instantiated for nstr in {2,4,6,8,12,16,24,32}; any other even nstr <= 32 is served by
   // the general kernel K3, whose sizes are run-time (one CTA per solve: correct, not tuned for throughput)
   const FluxInst* inst = inst_of(cfg->nstr);
+  if (std::getenv("B200DISORT_FORCE_GENERAL")) inst = nullptr;  // profiling knob: every solve on the general kernel
   if (!inst && cfg->nstr > 2 * kMaxNN) return B200DISORT_ERR_UNSUPPORTED;
   if ((cfg->flags & B200DISORT_USRTAU) && (cfg->ntau < 1 || !cfg->user_tau)) return B200DISORT_ERR_INVALID;
   const bool onlyfl = cfg->flags & B200DISORT_ONLYFL;
