@@ -106,3 +106,14 @@ extern "C" int hostsim_intensity(int nwave, int ncol, int nlyr, int nstr, int nm
   for (long s = 0; s < P.nlocal; ++s) solve_intensity_one(P, s, ws.data(), 0, 1);
   return 0;
 }
+
+// ---- small building blocks of the flux kernel, exposed for unit tests ----
+extern "C" int hostsim_pivot_bad(double d) {
+  PivotCheck c;
+  c.add(d);
+  return c.bad() ? 1 : 0;
+}
+
+extern "C" void hostsim_jacobi_rotation(double gpq, double gpp, double gqq, double eps2, double* tsc) {
+  jacobi_rotation(gpq, gpp, gqq, eps2, tsc[0], tsc[1], tsc[2]);
+}
