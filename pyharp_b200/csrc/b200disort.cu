@@ -340,6 +340,28 @@ static int ensure_dev(double** ptr, size_t* have, size_t need) {
   return B200DISORT_OK;
 }
 
+// Event ring behind b200disort_get_stats: one (begin, end) pair per timed solve-kernel launch on the handle's stream.
+static int ring_begin(b200disort_handle* h, cudaStream_t stream) {
+  if (h->ring_used == b200disort_handle::kRing) {  // fold the ring (blocks until those solves finished)
+    CU_TRY(cudaEventSynchronize(h->evB[h->ring_used - 1]));
+    for (int i = 0; i < h->ring_used; ++i) {
+      float ms = 0.f;
+      CU_TRY(cudaEventElapsedTime(&ms, h->evA[i], h->evB[i]));
+      h->ring_carry_ms += ms;
+    }
+    h->ring_used = 0;
+  }
+  CU_TRY(cudaEventRecord(h->evA[h->ring_used], stream));
+  return B200DISORT_OK;
+}
+
+static int ring_end(b200disort_handle* h, cudaStream_t stream) {
+  CU_TRY(cudaEventRecord(h->evB[h->ring_used], stream));
+  h->ring_used += 1;
+  h->solves_since_stats += 1;
+  return B200DISORT_OK;
+}
+
 // Launch the flux kernel for p.nlocal solves on `stream` with the given back-sweep workspace.
 // timed = record the launch in the handle's event ring (handle stream only).
 static int launch_flux(b200disort_handle* h, SolveParams& p, cudaStream_t stream, double** ws, size_t* ws_bytes,
@@ -365,22 +387,13 @@ static int launch_flux(b200disort_handle* h, SolveParams& p, cudaStream_t stream
   p.ws_threads = nthreads;
   p.ws_half = (long)half;
   if (timed) {
-    if (h->ring_used == b200disort_handle::kRing) {  // fold the ring (blocks until those solves finished)
-      CU_TRY(cudaEventSynchronize(h->evB[h->ring_used - 1]));
-      for (int i = 0; i < h->ring_used; ++i) {
-        float ms = 0.f;
-        CU_TRY(cudaEventElapsedTime(&ms, h->evA[i], h->evB[i]));
-        h->ring_carry_ms += ms;
-      }
-      h->ring_used = 0;
-    }
-    CU_TRY(cudaEventRecord(h->evA[h->ring_used], stream));
+    rc = ring_begin(h, stream);
+    if (rc != B200DISORT_OK) return rc;
   }
   CU_TRY(inst->launch(p, (unsigned)grid, block, stream));
   if (timed) {
-    CU_TRY(cudaEventRecord(h->evB[h->ring_used], stream));
-    h->ring_used += 1;
-    h->solves_since_stats += 1;
+    rc = ring_end(h, stream);
+    if (rc != B200DISORT_OK) return rc;
   }
   h->stats.kernel_launches += 1;
   h->stats.workspace_bytes = *ws_bytes;
@@ -445,7 +458,11 @@ static int solve_general(b200disort_handle* h, const double* prop, int nprop, co
   if (rc != B200DISORT_OK) return rc;
   P.ws = h->d_iws;
   P.s0 = 0; P.nlocal = nsolve;
+  rc = ring_begin(h, h->stream);  // the general kernel is timed like the flux kernel (b200disort_get_stats)
+  if (rc != B200DISORT_OK) return rc;
   CU_TRY(launch_intensity(P, (unsigned)grid, h->stream));
+  rc = ring_end(h, h->stream);
+  if (rc != B200DISORT_OK) return rc;
   h->stats.kernel_launches += 1;
   h->stats.workspace_bytes = h->iws_bytes;
   h->have_uu = nuu != 0;
