@@ -250,6 +250,10 @@ constexpr int kMaxSweeps = 16;
 #ifndef B200_SHARE_MAX_NN
 #define B200_SHARE_MAX_NN 4
 #endif
+// largest nn whose phase-function moments are loaded a layer ahead into registers (disort_solver_body.inc, PIPE_PM)
+#ifndef B200_PIPE_PM_MAX_NN
+#define B200_PIPE_PM_MAX_NN 4
+#endif
 #ifndef B200_BS_DEPTH
 #define B200_BS_DEPTH 3
 #endif
