@@ -132,6 +132,10 @@ int b200disort_reduce_band(b200disort_handle* h, const double* flx,
 
 int b200disort_get_stats(b200disort_handle* h, b200disort_stats* out);
 
+/* Change the cudaStream_t the handle launches on (NULL = default stream).  Waits for the work already queued on
+ * the previous stream, so buffers of earlier calls may be reused by the caller afterwards. */
+int b200disort_set_stream(b200disort_handle* h, void* stream);
+
 /* Measured FP64 FMA throughput of the device in TFLOP/s (a ~20 ms DFMA-saturating
  * kernel): the roofline denominator bench.py reports against. */
 int b200disort_fp64_peak(int device, double* tflops);

@@ -3,6 +3,8 @@ from .disort import (Disort, DisortOptions, DisortState, PhaseMomentOptions, sca
                      fp64_peak_tflops, IEX, ISS, IPM, IUP, IDN, kIsotropic, kRayleigh,
                      kHenyeyGreenstein)
 
-__all__ = ["Disort", "DisortOptions", "DisortState", "PhaseMomentOptions", "scattering_moments",
+from .band import RadiationBand, RadiationBandOptions  # noqa: E402
+
+__all__ = ["RadiationBand", "RadiationBandOptions", "Disort", "DisortOptions", "DisortState", "PhaseMomentOptions", "scattering_moments",
            "fp64_peak_tflops", "IEX", "ISS", "IPM", "IUP", "IDN", "kIsotropic", "kRayleigh",
            "kHenyeyGreenstein"]

@@ -34,10 +34,34 @@ class Stats(C.Structure):
                 ("total_device_ms", C.c_float), ("workspace_bytes", C.c_uint64)]
 
 
+class Attenuator(C.Structure):
+    """b200_attenuator (include/b200band.h)."""
+    _fields_ = [("type", C.c_int), ("species_id", C.c_int), ("kaxis", _dp), ("kdata", _dp), ("dims", C.c_int64 * 3),
+                ("klnp", _dp), ("ktemp", _dp), ("nref", C.c_int), ("kwave", _dp)]
+
+
+class BandConfig(C.Structure):
+    _fields_ = [("disort", Config), ("natt", C.c_int), ("att", C.POINTER(Attenuator)), ("nspecies", C.c_int),
+                ("wave", _dp), ("wave_is_wavenumber", C.c_int), ("weights", _dp), ("l2l_order", C.c_int),
+                ("l2l_blower", C.c_int), ("l2l_bupper", C.c_int), ("exact_interp", C.c_int), ("mix_eps", C.c_double),
+                ("host_chunk_cols", C.c_int)]
+
+
+class BandIO(C.Structure):
+    _fields_ = [("conc", C.c_void_p), ("pres", C.c_void_p), ("temp", C.c_void_p), ("dz", C.c_void_p), ("bc", BC),
+                ("bc_per_column", C.c_int), ("rho", C.c_void_p), ("cp", C.c_double), ("bflx", C.c_void_p),
+                ("dTdt", C.c_void_p), ("status", C.c_void_p), ("flx", C.c_void_p), ("prop", C.c_void_p)]
+
+
+ATT_RFM, ATT_AEROSOL = 1, 2
+
 EXPORTS = ("b200disort_create", "b200disort_solve", "b200disort_solve_host",
            "b200disort_check_status", "b200disort_get_rad", "b200disort_reduce_band",
-           "b200disort_get_stats", "b200disort_fp64_peak", "b200disort_destroy",
+           "b200disort_get_stats", "b200disort_set_stream", "b200disort_fp64_peak", "b200disort_destroy",
            "b200disort_strerror", "b200disort_version")
+BAND_EXPORTS = ("b200_band_create", "b200_band_nprop", "b200_band_optical_props", "b200_band_forward", "b200_band_forward_host", "b200_band_check",
+                "b200_band_allreduce", "b200_band_solver", "b200_band_destroy", "b200disort_allreduce_band",
+                "b200disort_solve_band")
 OPACITY_EXPORTS = ("b200_interpn", "b200_aerosol_optics", "b200_rfm_optics", "b200_layer2level", "b200_band_optics",
                    "b200_spherical_flux_correction", "b200_heating_rate")
 
@@ -93,6 +117,29 @@ def lib():
     L.b200_band_optics.restype = C.c_int
     L.b200_band_optics.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                    vp, vp]
+    # include/b200band.h
+    L.b200_band_create.restype = C.c_int
+    L.b200_band_create.argtypes = [C.POINTER(BandConfig), C.POINTER(vp)]
+    L.b200_band_nprop.restype = C.c_int
+    L.b200_band_nprop.argtypes = [vp]
+    for name in ("b200_band_forward", "b200_band_forward_host", "b200_band_optical_props"):
+        f = getattr(L, name)
+        f.restype = C.c_int
+        f.argtypes = [vp, C.POINTER(BandIO)]
+    L.b200_band_check.restype = C.c_int
+    L.b200_band_check.argtypes = [vp, C.POINTER(C.c_int)]
+    L.b200_band_allreduce.restype = C.c_int
+    L.b200_band_allreduce.argtypes = [vp, vp, C.c_long, vp]
+    L.b200_band_solver.restype = vp
+    L.b200_band_solver.argtypes = [vp]
+    L.b200_band_destroy.restype = None
+    L.b200_band_destroy.argtypes = [vp]
+    L.b200disort_allreduce_band.restype = C.c_int
+    L.b200disort_allreduce_band.argtypes = [vp, vp, vp]
+    L.b200disort_solve_band.restype = C.c_int
+    L.b200disort_solve_band.argtypes = [vp, vp, C.c_int, C.POINTER(BC), vp, vp, vp, vp]
+    L.b200disort_set_stream.restype = C.c_int
+    L.b200disort_set_stream.argtypes = [vp, vp]
     _lib = L
     return L
 

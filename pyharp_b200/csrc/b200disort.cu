@@ -14,9 +14,7 @@
 #include <utility>
 #include <vector>
 
-#include "../../include/b200disort.h"
-#include "disort_device.cuh"
-#include "flux_inst.cuh"
+#include "b200disort_internal.hpp"
 #include "host_tables.hpp"
 #include "intensity_device.cuh"
 #include "intensity_launch.hpp"
@@ -117,69 +115,6 @@ __global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
 
 using namespace b200;
 
-struct b200disort_handle {
-  b200disort_config cfg;
-  const b200::FluxInst* inst = nullptr;
-  cudaStream_t stream = nullptr;
-  int sm_count = 0;
-  int occ = 0;  // resident CTAs per SM of the flux kernel
-  std::vector<double> user_tau, user_mu, user_phi, wave_lower, wave_upper;
-  // device-side constants
-  double *d_wlo = nullptr, *d_whi = nullptr, *d_blo = nullptr, *d_bhi = nullptr;
-  int* d_w2b = nullptr;
-  int nband = 0;
-  double* d_pkag = nullptr;
-  size_t pkag_elems = 0;
-  double* d_ws = nullptr;
-  size_t ws_bytes = 0;
-  int* d_flag = nullptr;  // [0] planck bad-T flag, [1] bad status counter
-  // general (intensity / user-level) path
-  double *d_utau = nullptr, *d_umu = nullptr, *d_phi = nullptr, *d_quad = nullptr;  // d_quad = [cmu | cwt]
-  double* d_uu = nullptr;   // intensities of the last solve (nwave,ncol,nphi,ntau,numu)
-  size_t uu_bytes = 0;
-  double* d_iws = nullptr;  // per-CTA workspaces of the intensity kernel
-  size_t iws_bytes = 0;
-  bool have_uu = false;
-  double* d_part = nullptr;  // partial sums of reduce_band
-  size_t part_bytes = 0;
-  // host-pointer entry point: the batch is cut into chunks of solves that flow through kSlots
-  // independent (stream, device buffers, pinned staging) slots, so the H2D copy of chunk c+1, the
-  // solve of chunk c and the D2H copy of chunk c-1 run concurrently (copy engines + SMs).
-  static constexpr int kSlots = 3;
-  struct Slot {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t done = nullptr;
-    double* d_buf = nullptr;   // [inputs | flx | status]
-    size_t d_bytes = 0;
-    double* h_buf = nullptr;   // pinned staging, same layout; used only for pageable user memory
-    size_t h_bytes = 0;
-    double* d_ws = nullptr;
-    size_t ws_bytes = 0;
-    // pending copy-out of a finished chunk (pageable destination)
-    long pend_s0 = -1, pend_n = 0;
-  } slots[kSlots];
-  double* d_temf = nullptr;
-  size_t temf_bytes = 0;
-  cudaEvent_t ev_pre = nullptr;
-  // ring of event pairs around the solve kernel: get_stats sums every solve since the last call
-  static constexpr int kRing = 256;
-  cudaEvent_t ev0 = nullptr, evA[kRing] = {nullptr}, evB[kRing] = {nullptr};
-  int ring_used = 0;
-  double ring_carry_ms = 0.0;  // durations folded in when the ring wrapped
-  int solves_since_stats = 0;
-  b200disort_stats stats{};
-};
-
-#define CU_TRY(expr)                                                                         \
-  do {                                                                                       \
-    cudaError_t e__ = (expr);                                                                \
-    if (e__ != cudaSuccess) {                                                                \
-      std::fprintf(stderr, "b200disort: CUDA error '%s' at %s:%d\n", cudaGetErrorString(e__), \
-                   __FILE__, __LINE__);                                                      \
-      return B200DISORT_ERR_CUDA;                                                            \
-    }                                                                                        \
-  } while (0)
-
 static int nlev_out(const b200disort_config& c) {
   return (c.flags & B200DISORT_USRTAU) ? c.ntau : c.nlyr + 1;
 }
@@ -196,6 +131,84 @@ extern "C" const char* b200disort_strerror(int code) {
     default: return "unknown error";
   }
 }
+
+extern "C" void b200disort_destroy(b200disort_handle* h);
+// everything of b200disort_create that can fail after the handle exists; the caller destroys the handle on error
+static int init_handle(b200disort_handle* h, const b200disort_config* cfg) {
+  h->stream = (cudaStream_t)cfg->stream;
+  if (cfg->user_tau && cfg->ntau > 0) h->user_tau.assign(cfg->user_tau, cfg->user_tau + cfg->ntau);
+  if (cfg->user_mu && cfg->numu > 0) h->user_mu.assign(cfg->user_mu, cfg->user_mu + cfg->numu);
+  if (cfg->user_phi && cfg->nphi > 0) h->user_phi.assign(cfg->user_phi, cfg->user_phi + cfg->nphi);
+  if (cfg->wave_lower) h->wave_lower.assign(cfg->wave_lower, cfg->wave_lower + cfg->nwave);
+  if (cfg->wave_upper) h->wave_upper.assign(cfg->wave_upper, cfg->wave_upper + cfg->nwave);
+  h->cfg.user_tau = h->user_tau.data();
+  h->cfg.user_mu = h->user_mu.data();
+  h->cfg.user_phi = h->user_phi.data();
+  h->cfg.wave_lower = h->wave_lower.empty() ? nullptr : h->wave_lower.data();
+  h->cfg.wave_upper = h->wave_upper.empty() ? nullptr : h->wave_upper.data();
+
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  h->sm_count = prop.multiProcessorCount;
+
+  // constant tables for this stream count
+  QuadTables qt;
+  build_quad_tables(cfg->nstr, &qt);
+  if (h->inst) CU_TRY(h->inst->upload_tables(&qt));
+
+  // spectral bands: unique (wvnmlo, wvnmhi) pairs
+  if (!h->wave_lower.empty()) {
+    std::map<std::pair<double, double>, int> bands;
+    std::vector<int> w2b(cfg->nwave);
+    std::vector<double> blo, bhi;
+    for (int n = 0; n < cfg->nwave; ++n) {
+      auto key = std::make_pair(h->wave_lower[n], h->wave_upper[n]);
+      auto it = bands.find(key);
+      if (it == bands.end()) {
+        it = bands.emplace(key, (int)blo.size()).first;
+        blo.push_back(key.first);
+        bhi.push_back(key.second);
+      }
+      w2b[n] = it->second;
+      if (!(key.first >= 0.0) || !(key.second >= key.first)) return B200DISORT_ERR_INVALID;
+    }
+    h->nband = (int)blo.size();
+    CU_TRY(cudaMalloc(&h->d_wlo, sizeof(double) * cfg->nwave));
+    CU_TRY(cudaMalloc(&h->d_whi, sizeof(double) * cfg->nwave));
+    CU_TRY(cudaMalloc(&h->d_blo, sizeof(double) * h->nband));
+    CU_TRY(cudaMalloc(&h->d_bhi, sizeof(double) * h->nband));
+    CU_TRY(cudaMalloc(&h->d_w2b, sizeof(int) * cfg->nwave));
+    CU_TRY(cudaMemcpy(h->d_wlo, h->wave_lower.data(), sizeof(double) * cfg->nwave, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(h->d_whi, h->wave_upper.data(), sizeof(double) * cfg->nwave, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(h->d_blo, blo.data(), sizeof(double) * h->nband, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(h->d_bhi, bhi.data(), sizeof(double) * h->nband, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(h->d_w2b, w2b.data(), sizeof(int) * cfg->nwave, cudaMemcpyHostToDevice));
+  }
+  {
+    auto up = [&](const std::vector<double>& v, double** d) -> int {
+      if (v.empty()) return B200DISORT_OK;
+      CU_TRY(cudaMalloc(d, sizeof(double) * v.size()));
+      CU_TRY(cudaMemcpy(*d, v.data(), sizeof(double) * v.size(), cudaMemcpyHostToDevice));
+      return B200DISORT_OK;
+    };
+    std::vector<double> quad(cfg->nstr);
+    for (int i = 0; i < cfg->nstr / 2; ++i) { quad[i] = qt.mu[i]; quad[cfg->nstr / 2 + i] = qt.wt[i]; }
+    int rc = up(h->user_tau, &h->d_utau);
+    if (rc == B200DISORT_OK) rc = up(h->user_mu, &h->d_umu);
+    if (rc == B200DISORT_OK) rc = up(h->user_phi, &h->d_phi);
+    if (rc == B200DISORT_OK) rc = up(quad, &h->d_quad);
+    if (rc != B200DISORT_OK) return rc;
+  }
+  CU_TRY(cudaMalloc(&h->d_flag, sizeof(int) * 2));
+  CU_TRY(cudaMemset(h->d_flag, 0, sizeof(int) * 2));
+  CU_TRY(cudaEventCreate(&h->ev0));
+  for (int i = 0; i < b200disort_handle::kRing; ++i) {
+    CU_TRY(cudaEventCreate(&h->evA[i]));
+    CU_TRY(cudaEventCreate(&h->evB[i]));
+  }
+  return B200DISORT_OK;
+}
+
 
 extern "C" int b200disort_create(const b200disort_config* cfg, b200disort_handle** out) {
   if (!cfg || !out) return B200DISORT_ERR_INVALID;
@@ -226,79 +239,10 @@ extern "C" int b200disort_create(const b200disort_config* cfg, b200disort_handle
   if (!h) return B200DISORT_ERR_INVALID;
   h->cfg = *cfg;
   h->inst = inst;
-  h->stream = (cudaStream_t)cfg->stream;
-  if (cfg->user_tau && cfg->ntau > 0) h->user_tau.assign(cfg->user_tau, cfg->user_tau + cfg->ntau);
-  if (cfg->user_mu && cfg->numu > 0) h->user_mu.assign(cfg->user_mu, cfg->user_mu + cfg->numu);
-  if (cfg->user_phi && cfg->nphi > 0) h->user_phi.assign(cfg->user_phi, cfg->user_phi + cfg->nphi);
-  if (cfg->wave_lower) h->wave_lower.assign(cfg->wave_lower, cfg->wave_lower + cfg->nwave);
-  if (cfg->wave_upper) h->wave_upper.assign(cfg->wave_upper, cfg->wave_upper + cfg->nwave);
-  h->cfg.user_tau = h->user_tau.data();
-  h->cfg.user_mu = h->user_mu.data();
-  h->cfg.user_phi = h->user_phi.data();
-  h->cfg.wave_lower = h->wave_lower.empty() ? nullptr : h->wave_lower.data();
-  h->cfg.wave_upper = h->wave_upper.empty() ? nullptr : h->wave_upper.data();
-
-  cudaDeviceProp prop;
-  CU_TRY(cudaGetDeviceProperties(&prop, cfg->device));
-  h->sm_count = prop.multiProcessorCount;
-
-  // constant tables for this stream count
-  QuadTables qt;
-  build_quad_tables(cfg->nstr, &qt);
-  if (inst) CU_TRY(inst->upload_tables(&qt));
-
-  // spectral bands: unique (wvnmlo, wvnmhi) pairs
-  if (!h->wave_lower.empty()) {
-    std::map<std::pair<double, double>, int> bands;
-    std::vector<int> w2b(cfg->nwave);
-    std::vector<double> blo, bhi;
-    for (int n = 0; n < cfg->nwave; ++n) {
-      auto key = std::make_pair(h->wave_lower[n], h->wave_upper[n]);
-      auto it = bands.find(key);
-      if (it == bands.end()) {
-        it = bands.emplace(key, (int)blo.size()).first;
-        blo.push_back(key.first);
-        bhi.push_back(key.second);
-      }
-      w2b[n] = it->second;
-      if (!(key.first >= 0.0) || !(key.second >= key.first)) {
-        delete h;
-        return B200DISORT_ERR_INVALID;
-      }
-    }
-    h->nband = (int)blo.size();
-    CU_TRY(cudaMalloc(&h->d_wlo, sizeof(double) * cfg->nwave));
-    CU_TRY(cudaMalloc(&h->d_whi, sizeof(double) * cfg->nwave));
-    CU_TRY(cudaMalloc(&h->d_blo, sizeof(double) * h->nband));
-    CU_TRY(cudaMalloc(&h->d_bhi, sizeof(double) * h->nband));
-    CU_TRY(cudaMalloc(&h->d_w2b, sizeof(int) * cfg->nwave));
-    CU_TRY(cudaMemcpy(h->d_wlo, h->wave_lower.data(), sizeof(double) * cfg->nwave, cudaMemcpyHostToDevice));
-    CU_TRY(cudaMemcpy(h->d_whi, h->wave_upper.data(), sizeof(double) * cfg->nwave, cudaMemcpyHostToDevice));
-    CU_TRY(cudaMemcpy(h->d_blo, blo.data(), sizeof(double) * h->nband, cudaMemcpyHostToDevice));
-    CU_TRY(cudaMemcpy(h->d_bhi, bhi.data(), sizeof(double) * h->nband, cudaMemcpyHostToDevice));
-    CU_TRY(cudaMemcpy(h->d_w2b, w2b.data(), sizeof(int) * cfg->nwave, cudaMemcpyHostToDevice));
-  }
-  {
-    auto up = [&](const std::vector<double>& v, double** d) -> int {
-      if (v.empty()) return B200DISORT_OK;
-      CU_TRY(cudaMalloc(d, sizeof(double) * v.size()));
-      CU_TRY(cudaMemcpy(*d, v.data(), sizeof(double) * v.size(), cudaMemcpyHostToDevice));
-      return B200DISORT_OK;
-    };
-    std::vector<double> quad(cfg->nstr);
-    for (int i = 0; i < cfg->nstr / 2; ++i) { quad[i] = qt.mu[i]; quad[cfg->nstr / 2 + i] = qt.wt[i]; }
-    int rc = up(h->user_tau, &h->d_utau);
-    if (rc == B200DISORT_OK) rc = up(h->user_mu, &h->d_umu);
-    if (rc == B200DISORT_OK) rc = up(h->user_phi, &h->d_phi);
-    if (rc == B200DISORT_OK) rc = up(quad, &h->d_quad);
-    if (rc != B200DISORT_OK) { delete h; return rc; }
-  }
-  CU_TRY(cudaMalloc(&h->d_flag, sizeof(int) * 2));
-  CU_TRY(cudaMemset(h->d_flag, 0, sizeof(int) * 2));
-  CU_TRY(cudaEventCreate(&h->ev0));
-  for (int i = 0; i < b200disort_handle::kRing; ++i) {
-    CU_TRY(cudaEventCreate(&h->evA[i]));
-    CU_TRY(cudaEventCreate(&h->evB[i]));
+  const int rc = init_handle(h, cfg);
+  if (rc != B200DISORT_OK) {  // release whatever was allocated before the failure
+    b200disort_destroy(h);
+    return rc;
   }
   *out = h;
   return B200DISORT_OK;
@@ -310,7 +254,7 @@ extern "C" void b200disort_destroy(b200disort_handle* h) {
   cudaStreamSynchronize(h->stream);
   cudaFree(h->d_wlo); cudaFree(h->d_whi); cudaFree(h->d_blo); cudaFree(h->d_bhi);
   cudaFree(h->d_w2b); cudaFree(h->d_pkag); cudaFree(h->d_ws); cudaFree(h->d_flag);
-  cudaFree(h->d_part); cudaFree(h->d_temf);
+  cudaFree(h->d_part); cudaFree(h->d_temf); cudaFree(h->d_acc);
   cudaFree(h->d_utau); cudaFree(h->d_umu); cudaFree(h->d_phi); cudaFree(h->d_quad); cudaFree(h->d_uu); cudaFree(h->d_iws);
   for (auto& sl : h->slots) {
     if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
@@ -330,7 +274,7 @@ extern "C" void b200disort_destroy(b200disort_handle* h) {
 constexpr long kHostChunkDiv = 1;  // host-path chunk = resident wave / kHostChunkDiv
 
 // grow-only device buffer
-static int ensure_dev(double** ptr, size_t* have, size_t need) {
+int b200::ensure_dev(double** ptr, size_t* have, size_t need) {
   if (need <= *have) return B200DISORT_OK;
   if (*ptr) CU_TRY(cudaFree(*ptr));
   *ptr = nullptr;
@@ -364,8 +308,8 @@ static int ring_end(b200disort_handle* h, cudaStream_t stream) {
 
 // Launch the flux kernel for p.nlocal solves on `stream` with the given back-sweep workspace.
 // timed = record the launch in the handle's event ring (handle stream only).
-static int launch_flux(b200disort_handle* h, SolveParams& p, cudaStream_t stream, double** ws, size_t* ws_bytes,
-                       bool timed) {
+int b200::launch_flux(b200disort_handle* h, SolveParams& p, cudaStream_t stream, double** ws, size_t* ws_bytes,
+                      bool timed) {
   const FluxInst* inst = h->inst;
   // tuning knobs (profiling only): B200DISORT_BLOCK = threads per CTA (<= 128), B200DISORT_CTAS_PER_SM caps residency
   static const int env_block = std::getenv("B200DISORT_BLOCK") ? std::atoi(std::getenv("B200DISORT_BLOCK")) : 0;
@@ -400,6 +344,17 @@ static int launch_flux(b200disort_handle* h, SolveParams& p, cudaStream_t stream
   return B200DISORT_OK;
 }
 
+int b200::launch_planck_into(b200disort_handle* h, const double* temf, int ncol, double* pkag, cudaStream_t stream) {
+  const size_t elems = (size_t)h->nband * ncol * (h->cfg.nlyr + 1);
+  const int block = 256;
+  const long grid = std::min<long>((long)((elems + block - 1) / block), (long)h->sm_count * 8);
+  planck_prepass_kernel<<<(unsigned)grid, block, 0, stream>>>(h->nband, ncol, h->cfg.nlyr, h->d_blo, h->d_bhi, temf, pkag,
+                                                             h->d_flag);
+  CU_TRY(cudaGetLastError());
+  h->stats.kernel_launches += 1;
+  return B200DISORT_OK;
+}
+
 // Planck pre-pass on `stream`: temf (device) -> h->d_pkag
 static int launch_planck(b200disort_handle* h, const double* temf, cudaStream_t stream) {
   const b200disort_config& c = h->cfg;
@@ -408,12 +363,12 @@ static int launch_planck(b200disort_handle* h, const double* temf, cudaStream_t 
   int rc = ensure_dev(&h->d_pkag, &have, elems * sizeof(double));
   h->pkag_elems = have / sizeof(double);
   if (rc != B200DISORT_OK) return rc;
-  const int block = 256;
-  const long grid = std::min<long>((long)((elems + block - 1) / block), (long)h->sm_count * 8);
-  planck_prepass_kernel<<<(unsigned)grid, block, 0, stream>>>(h->nband, c.ncol, c.nlyr, h->d_blo, h->d_bhi, temf,
-                                                             h->d_pkag, h->d_flag);
+  return launch_planck_into(h, temf, c.ncol, h->d_pkag, stream);
+}
+
+int b200::launch_count_status(b200disort_handle* h, const int32_t* status, long n, cudaStream_t stream) {
+  count_status_kernel<<<(unsigned)std::min<long>((n + 255) / 256, 1024), 256, 0, stream>>>(status, n, h->d_flag + 1);
   CU_TRY(cudaGetLastError());
-  h->stats.kernel_launches += 1;
   return B200DISORT_OK;
 }
 
@@ -531,13 +486,23 @@ extern "C" int b200disort_get_stats(b200disort_handle* h, b200disort_stats* out)
   return B200DISORT_OK;
 }
 
+extern "C" int b200disort_set_stream(b200disort_handle* h, void* stream) {
+  if (!h) return B200DISORT_ERR_INVALID;
+  if (h->stream == (cudaStream_t)stream) return B200DISORT_OK;
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  h->stream = (cudaStream_t)stream;
+  h->cfg.stream = stream;
+  return B200DISORT_OK;
+}
+
 extern "C" int b200disort_check_status(b200disort_handle* h, const int32_t* status, int* n_bad) {
   if (!h || !status || !n_bad) return B200DISORT_ERR_INVALID;
   CU_TRY(cudaSetDevice(h->cfg.device));
   const long n = (long)h->cfg.nwave * h->cfg.ncol;
   CU_TRY(cudaMemsetAsync(h->d_flag + 1, 0, sizeof(int), h->stream));
-  count_status_kernel<<<(unsigned)std::min<long>((n + 255) / 256, 1024), 256, 0, h->stream>>>(status, n, h->d_flag + 1);
-  CU_TRY(cudaGetLastError());
+  int rc = launch_count_status(h, status, n, h->stream);
+  if (rc != B200DISORT_OK) return rc;
   int flags[2] = {0, 0};
   CU_TRY(cudaMemcpyAsync(flags, h->d_flag, sizeof(int) * 2, cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(cudaStreamSynchronize(h->stream));
@@ -549,7 +514,7 @@ extern "C" int b200disort_check_status(b200disort_handle* h, const int32_t* stat
   return flags[1] ? B200DISORT_ERR_SOLVE : B200DISORT_OK;
 }
 
-static bool is_pinned(const void* p) {
+bool b200::is_pinned(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
     cudaGetLastError();
@@ -781,19 +746,15 @@ extern "C" int b200disort_get_rad(b200disort_handle* h, double* uu) {
   return B200DISORT_OK;
 }
 
-extern "C" int b200disort_reduce_band(b200disort_handle* h, const double* flx, const double* weights,
-                                      double* bflx) {
-  if (!h || !flx || !weights || !bflx) return B200DISORT_ERR_INVALID;
-  const b200disort_config& c = h->cfg;
-  CU_TRY(cudaSetDevice(c.device));
-  const long inner = (long)c.ncol * nlev_out(c) * 2;
+int b200::launch_reduce_band(b200disort_handle* h, int nwave, long inner, const double* flx, const double* weights,
+                             double* bflx, cudaStream_t stream) {
   const int block = 256;
   const long grid = std::min<long>((inner + block - 1) / block, (long)h->sm_count * 8);
   const long want = (long)h->sm_count * 8;  // CTAs that fill the machine
   int parts = (int)std::min<long>(std::max<long>(1, want / std::max<long>(1, (inner + block - 1) / block)),
-                                  std::max(1, c.nwave / 16));
+                                  std::max(1, nwave / 16));
   if (parts <= 1) {
-    reduce_band_kernel<<<dim3((unsigned)grid, 1), block, 0, h->stream>>>(c.nwave, inner, flx, weights, bflx);
+    reduce_band_kernel<<<dim3((unsigned)grid, 1), block, 0, stream>>>(nwave, inner, flx, weights, bflx);
     CU_TRY(cudaGetLastError());
     return B200DISORT_OK;
   }
@@ -805,11 +766,19 @@ extern "C" int b200disort_reduce_band(b200disort_handle* h, const double* flx, c
     CU_TRY(cudaMalloc(&h->d_part, need));
     h->part_bytes = need;
   }
-  reduce_band_kernel<<<dim3((unsigned)grid, (unsigned)parts), block, 0, h->stream>>>(c.nwave, inner, flx, weights, h->d_part);
+  reduce_band_kernel<<<dim3((unsigned)grid, (unsigned)parts), block, 0, stream>>>(nwave, inner, flx, weights, h->d_part);
   CU_TRY(cudaGetLastError());
-  reduce_parts_kernel<<<(unsigned)grid, block, 0, h->stream>>>(parts, inner, h->d_part, bflx);
+  reduce_parts_kernel<<<(unsigned)grid, block, 0, stream>>>(parts, inner, h->d_part, bflx);
   CU_TRY(cudaGetLastError());
   return B200DISORT_OK;
+}
+
+extern "C" int b200disort_reduce_band(b200disort_handle* h, const double* flx, const double* weights,
+                                      double* bflx) {
+  if (!h || !flx || !weights || !bflx) return B200DISORT_ERR_INVALID;
+  const b200disort_config& c = h->cfg;
+  CU_TRY(cudaSetDevice(c.device));
+  return launch_reduce_band(h, c.nwave, (long)c.ncol * nlev_out(c) * 2, flx, weights, bflx, h->stream);
 }
 
 extern "C" int b200disort_fp64_peak(int device, double* tflops) {

@@ -66,6 +66,34 @@ __device__ __forceinline__ double b200_fast_rsqrt(double x) {
 #define B200_RCP(x) __drcp_rn(x)
 #define B200_RSQRT(x) rsqrt(x)
 #endif
+// 1 - exp(-y) for y >= 0 with full RELATIVE accuracy (the -expm1(-y) of the math library, straight-line: range
+// reduction -y = n ln 2 + r, Taylor polynomial of expm1(r) on |r| <= ln 2 / 2, 1 - 2^n (1 + expm1 r) in one FMA).
+// The layer transmission functions k coth(k dtau'/2), k tanh(k dtau'/2) are formed from it; "1.0 - exp(-y)" has an
+// absolute error of 1e-16, i.e. a relative one of 1e-16 / y, and the thermal source of a layer divides by dtau':
+// across layers of dtau' ~ 1e-9 (upper atmosphere of a weak correlated-k g-point) that cost 7 digits of the flux.
+__device__ __forceinline__ double b200_one_minus_exp_neg(double y) {
+  const double x = fmax(-y, -700.0);  // exp(-700) = 1e-304: the result is 1 to double precision beyond
+  const double n = rint(x * 1.4426950408889634);
+  double r = fma(n, -6.93147180559945286e-01, x);
+  r = fma(n, -2.31904681384629956e-17, r);
+  double p = 1.0 / 87178291200.0;  // 1 / 14!
+  p = fma(p, r, 1.0 / 6227020800.0);
+  p = fma(p, r, 1.0 / 479001600.0);
+  p = fma(p, r, 1.0 / 39916800.0);
+  p = fma(p, r, 1.0 / 3628800.0);
+  p = fma(p, r, 1.0 / 362880.0);
+  p = fma(p, r, 1.0 / 40320.0);
+  p = fma(p, r, 1.0 / 5040.0);
+  p = fma(p, r, 1.0 / 720.0);
+  p = fma(p, r, 1.0 / 120.0);
+  p = fma(p, r, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  const double q = fma(p * r, r, r);  // expm1(r)
+  const double s = __hiloint2double(((int)n + 1023) << 20, 0);  // 2^n, n in [-1010, 0]
+  return fma(-s, q, 1.0 - s);
+}
+#define B200_EM(y) b200_one_minus_exp_neg(y)
 #define B200_PREFETCH(ptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr))
 #define B200_HIWORD(x) __double2hiint(x)
 // Streaming (evict-first) accesses for the back-sweep records, which are written once and read once.  At nstr >= 12 the kernel spills ~3 KB per thread, and the
@@ -103,6 +131,7 @@ __device__ __forceinline__ double b200_fast_rsqrt(double x) {
 #define B200_PREFETCH(ptr) ((void)0)
 #define B200_RCP(x) (1.0 / (x))
 #define B200_RSQRT(x) (1.0 / sqrt(x))
+#define B200_EM(y) (-expm1(-(y)))
 #define B200_HIWORD(x) b200::host_hiword(x)
 #define B200_ST_STREAM(ptr, v) (*(ptr) = (v))
 #define B200_LD_STREAM(ptr) (*(ptr))
@@ -153,6 +182,14 @@ struct SolveParams {
   int32_t* status; // (nwave,ncol)
   long s0;         // batch index of this launch's first solve (chunked host path); prop/bc/flx/status are chunk-local
   long nlocal;     // solves in this launch
+  // BAND instantiation (fused band integration, examples/amars_lw.cpp:84-88): instead of the per-spectral-point
+  // flux rows the kernel accumulates w_n F_n into bflx_t[(row * 2 + c) * ncol + j] (row = pyharp level index, level
+  // 0 = surface; coalesced across the lanes of a warp, which are neighbouring columns) with FP64 reductions in the
+  // L2; flx is not written.  The host zeroes bflx_t before the launch.
+  double* bflx_t;
+  const double* weights;  // (nwave) band weights (BAND only)
+  int bc_bcast;    // != 0: the boundary fields are (ncol) arrays shared by every spectral point
+  int warp_red;    // BAND = 2: columns per warp (= ncol, a power of two <= 16), see emit_flux
   double* ws;      // back-sweep workspace: [half][warp][level][elem][lane] (kWsLanes lanes per group)
   long ws_half;    // doubles per half (carried back sweep: two halves; otherwise unused)
   long ws_threads; // threads the workspace was sized for (a multiple of kWsLanes)
@@ -371,10 +408,58 @@ __device__ __forceinline__ void b200_mbar_wait(unsigned long long* bar, unsigned
 template <int NN>
 constexpr bool kCarryBack = B200_CARRY_BACK && NN >= 4 && TmaRing<NN * NN + 2 * NN + 1>::kUsed;
 
+// One output level of a solve: row = pyharp level index (0 = surface).
+//   BAND = 0  the per-solve flux row;
+//   BAND = 1  fused band integration: w_n F_n accumulated into the band-flux buffer with FP64 reductions in the L2
+//             (RED.E.ADD.F64; the summation order over spectral points is not fixed -- a few ulp between runs);
+//   BAND = 2  the same when fewer than 32 columns share the batch (line-by-line: 10^5 spectral points x 1 column), so
+//             that the lanes of a warp are spectral points of the SAME column: the warp first adds its lanes' terms
+//             per column with shuffles (p.warp_red = ncol, a power of two <= 16; lane l holds column l % ncol) and
+//             only `ncol` lanes touch the L2 -- 32 same-address reductions per instruction would serialise there.
+//             Must be reached by all 32 lanes with a warp-uniform row; `pred` masks lanes without a value.
+constexpr int kBandOff = 0, kBandAtomic = 1, kBandWarpRed = 2;
+template <int BAND>
+B200_HD void emit_flux(double* out, int row, long stride, double wg, double fup, double fdn, bool pred, int warp_red) {
+  if constexpr (BAND == kBandOff) {
+    if (pred) {
+      out[2 * row] = fup;
+      out[2 * row + 1] = fdn;
+    }
+    (void)stride; (void)wg; (void)warp_red;
+  } else {
+#if defined(__CUDA_ARCH__)
+    if constexpr (BAND == kBandWarpRed) {
+      double a = pred ? wg * fup : 0.0, b = pred ? wg * fdn : 0.0;
+      for (int o = 16; o >= warp_red; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if ((int)(threadIdx.x & 31) < warp_red) {
+        atomicAdd(out + (long)(2 * row) * stride, a);
+        atomicAdd(out + (long)(2 * row + 1) * stride, b);
+      }
+    } else {
+      if (pred) {
+        atomicAdd(out + (long)(2 * row) * stride, wg * fup);
+        atomicAdd(out + (long)(2 * row + 1) * stride, wg * fdn);
+      }
+      (void)warp_red;
+    }
+#else
+    if (pred) {
+      out[(long)(2 * row) * stride] += wg * fup;
+      out[(long)(2 * row + 1) * stride] += wg * fdn;
+    }
+    (void)warp_red;
+#endif
+  }
+}
+
 template <int NN>
 struct BackPend {
   double up[NN];           // upward radiation at level lev + 1
-  double* out = nullptr;   // flux rows of the pending solve
+  double wg = 0.0;         // BAND: band weight of the pending solve
+  double* out = nullptr;   // flux rows of the pending solve (BAND: its column in the band-flux buffer)
   const double* wsl = nullptr;  // lane base (level 0) of its workspace half
   int ncut = 0;            // this lane emits levels lev < ncut
   int lev = -1;            // warp-uniform: next level to emit, counting down; < 0: nothing pending
@@ -435,23 +520,23 @@ B200_HD constexpr int bl_src(int i, int n) {
 #undef B200_FN
 
 // NOMOM = the launch carries no phase-function moments (nprop <= 2): isotropic scattering, compile-time lmax = 1
-template <int NN, bool NOMOM = false, typename QT>
+template <int NN, bool NOMOM = false, int BAND = 0, typename QT>
 B200_HD void solve_flux_one(const SolveParams& p, const QT& qt, long s, long tid, bool active, unsigned& ring_pos,
                             BackPend<NN>& pend, int wshalf) {
 #ifndef B200_UNROLL_MAX_NN
 #define B200_UNROLL_MAX_NN 4
 #endif
-  if constexpr (NN <= B200_UNROLL_MAX_NN) solve_flux_one_u<NN, NOMOM>(p, qt, s, tid, active, ring_pos, pend, wshalf);
-  else solve_flux_one_r<NN, NOMOM>(p, qt, s, tid, active, ring_pos, pend, wshalf);
+  if constexpr (NN <= B200_UNROLL_MAX_NN) solve_flux_one_u<NN, NOMOM, BAND>(p, qt, s, tid, active, ring_pos, pend, wshalf);
+  else solve_flux_one_r<NN, NOMOM, BAND>(p, qt, s, tid, active, ring_pos, pend, wshalf);
 }
 
 // finishes a pending (carried) back sweep after a thread's last solve
-template <int NN, typename QT>
-B200_HD void drain_back_sweep(BackPend<NN>& pend, const QT& qt, long tid, unsigned& ring_pos) {
+template <int NN, int BAND = 0, typename QT>
+B200_HD void drain_back_sweep(const SolveParams& p, BackPend<NN>& pend, const QT& qt, long tid, unsigned& ring_pos) {
   if constexpr (NN <= B200_UNROLL_MAX_NN) {
-    while (pend.lev >= 0) back_level_u<NN>(pend, qt, tid, ring_pos);
+    while (pend.lev >= 0) back_level_u<NN, BAND>(p, pend, qt, tid, ring_pos);
   } else {
-    while (pend.lev >= 0) back_level_r<NN>(pend, qt, tid, ring_pos);
+    while (pend.lev >= 0) back_level_r<NN, BAND>(p, pend, qt, tid, ring_pos);
   }
 }
 

@@ -51,7 +51,14 @@ constexpr int kNsave = B200_NN * B200_NN + 2 * B200_NN + 1;
 #else
 #define B200_HAVE_NOMOM 0  // large stream counts always come with moments; one (large) kernel is enough
 #endif
-template <bool NOMOM>
+// BAND: fused band integration -- w_n F_n accumulated per column instead of per-solve flux rows (SolveParams::bflx_t,
+// emit_flux in disort_device.cuh); BAND = 2 is the form for batches of fewer than 32 columns (nstr <= 8 only)
+#if B200_NN <= 4
+#define B200_HAVE_WARPRED 1
+#else
+#define B200_HAVE_WARPRED 0
+#endif
+template <bool NOMOM, int BAND>
 __global__ void __launch_bounds__(B200_MAX_THREADS, B200_MIN_BLOCKS) disort_flux_kernel(SolveParams p) {
   const long nthreads = (long)gridDim.x * blockDim.x;
   const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -77,11 +84,11 @@ __global__ void __launch_bounds__(B200_MAX_THREADS, B200_MIN_BLOCKS) disort_flux
   for (long base = (long)blockIdx.x * blockDim.x; base < nsolve; base += nthreads, ++it) {
     const long s = base + threadIdx.x;
     const bool active = s < nsolve;
-    solve_flux_one<B200_NN, NOMOM>(p, c_qt, active ? s : nsolve - 1, tid, active, ring_pos, pend, it & 1);
+    solve_flux_one<B200_NN, NOMOM, BAND>(p, c_qt, active ? s : nsolve - 1, tid, active, ring_pos, pend, it & 1);
   }
   if constexpr (kCarryBack<B200_NN>) {
     __syncwarp();
-    drain_back_sweep<B200_NN>(pend, c_qt, tid, ring_pos);
+    drain_back_sweep<B200_NN, BAND>(p, pend, c_qt, tid, ring_pos);
   }
 }
 
@@ -101,23 +108,51 @@ size_t smem_bytes(int block) {
 cudaError_t occupancy(int block, int* blocks_per_sm) {
   const size_t sm = smem_bytes(block);
   if (sm > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(disort_flux_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    if (e != cudaSuccess) return e;
-#if B200_HAVE_NOMOM
-    e = cudaFuncSetAttribute(disort_flux_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    if (e != cudaSuccess) return e;
-#endif
+#define B200_SET_SMEM(NOMOM, BAND)                                                                                  \
+  {                                                                                                                 \
+    cudaError_t e = cudaFuncSetAttribute(disort_flux_kernel<NOMOM, BAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)sm);                                                                  \
+    if (e != cudaSuccess) return e;                                                                                 \
   }
-  // (the no-moments instantiation never needs more registers than the general one)
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, disort_flux_kernel<false>, block, sm);
+    B200_SET_SMEM(false, 0) B200_SET_SMEM(false, 1)
+#if B200_HAVE_WARPRED
+    B200_SET_SMEM(false, 2)
+#endif
+#if B200_HAVE_NOMOM
+    B200_SET_SMEM(true, 0) B200_SET_SMEM(true, 1)
+#if B200_HAVE_WARPRED
+    B200_SET_SMEM(true, 2)
+#endif
+#endif
+#undef B200_SET_SMEM
+  }
+  // (all instantiations run under the same __launch_bounds__, hence the same residency)
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, disort_flux_kernel<false, 0>, block, sm);
 }
 
 cudaError_t launch(const SolveParams& p, unsigned grid, int block, cudaStream_t stream) {
+  // band mode: plain L2 reductions, or warp-reduced ones when the lanes of a warp share columns (p.warp_red > 0,
+  // set by the host for ncol in {1, 2, 4, 8, 16}; only the nstr <= 8 kernels have that form)
+  const int band = !p.bflx_t ? 0 : (B200_HAVE_WARPRED && p.warp_red > 0) ? 2 : 1;
+  const size_t sm = smem_bytes(block);
+#define B200_LAUNCH(NOMOM, BAND) disort_flux_kernel<NOMOM, BAND><<<grid, block, sm, stream>>>(p)
 #if B200_HAVE_NOMOM
-  if (p.nprop <= 2) disort_flux_kernel<true><<<grid, block, smem_bytes(block), stream>>>(p);
-  else
+  if (p.nprop <= 2) {
+    if (band == 0) B200_LAUNCH(true, 0);
+    else if (band == 1) B200_LAUNCH(true, 1);
+#if B200_HAVE_WARPRED
+    else B200_LAUNCH(true, 2);
 #endif
-    disort_flux_kernel<false><<<grid, block, smem_bytes(block), stream>>>(p);
+  } else
+#endif
+  {
+    if (band == 0) B200_LAUNCH(false, 0);
+    else if (band == 1) B200_LAUNCH(false, 1);
+#if B200_HAVE_WARPRED
+    else B200_LAUNCH(false, 2);
+#endif
+  }
+#undef B200_LAUNCH
   return cudaGetLastError();
 }
 

@@ -7,62 +7,9 @@
 #include <cstdio>
 
 #include "../../include/b200opacity.h"
+#include "opacity_device.cuh"
 
 namespace b200 {
-
-// harp::locate (src/math/locate.h:14-42): bisection on a monotonic table, exact-endpoint rule.
-__device__ __forceinline__ int locate_dev(const double* xx0, double x, int n) {
-  const double* xx = xx0 - 1;
-  int jl = 0, ju = n + 1;
-  const bool ascnd = (xx[n] >= xx[1]);
-  while (ju - jl > 1) {
-    const int jm = (ju + jl) >> 1;
-    if ((x >= xx[jm]) == ascnd) jl = jm;
-    else ju = jm;
-  }
-  int j;
-  if (x == xx[1]) j = 1;
-  else if (x == xx[n]) j = n;
-  else j = jl;
-  return j - 1;
-}
-
-struct Dims {
-  long len[4];
-  long stride[4];  // elements of `data` per step along each dimension (includes nval)
-  long axis_off[4];
-};
-
-// harp::interpn<N> (src/math/interpn.h:34-76) with the recursion unrolled over NDIM; the blend uses
-// explicit round-to-nearest mul/add so nvcc cannot contract it into FMAs (bit parity with the CPU path).
-template <int NDIM, int NVAL>
-__device__ void interpn_dev(double* val, const double* coor, const double* data, const double* axis, const Dims& d,
-                            int dim0) {
-  const long len = d.len[dim0];
-  const double* ax = axis + d.axis_off[dim0];
-  const double c = coor[0];
-  int i1 = locate_dev(ax, c, (int)len), i2;
-  if (i1 == -1) { i1 = 0; i2 = 0; }
-  else if (i1 == len - 1) { i2 = (int)len - 1; }
-  else i2 = i1 + 1;
-  double v1[NVAL], v2[NVAL];
-  const double x1 = ax[i1], x2 = ax[i2];
-  if constexpr (NDIM == 1) {
-#pragma unroll
-    for (int j = 0; j < NVAL; ++j) { v1[j] = data[i1 * d.stride[dim0] + j]; v2[j] = data[i2 * d.stride[dim0] + j]; }
-  } else {
-    interpn_dev<NDIM - 1, NVAL>(v1, coor + 1, data + i1 * d.stride[dim0], axis, d, dim0 + 1);
-    interpn_dev<NDIM - 1, NVAL>(v2, coor + 1, data + i2 * d.stride[dim0], axis, d, dim0 + 1);
-  }
-  if (x2 != x1) {
-    const double a = __dsub_rn(c, x1), b = __dsub_rn(x2, c), den = __dsub_rn(x2, x1);
-#pragma unroll
-    for (int j = 0; j < NVAL; ++j) val[j] = __ddiv_rn(__dadd_rn(__dmul_rn(a, v2[j]), __dmul_rn(b, v1[j])), den);
-  } else {
-#pragma unroll
-    for (int j = 0; j < NVAL; ++j) val[j] = __ddiv_rn(__dadd_rn(v1[j], v2[j]), 2.0);
-  }
-}
 
 template <int NDIM, int NVAL>
 __global__ void interpn_kernel(const double* __restrict__ coord, long npoint, long cstride, const double* __restrict__ data,
@@ -175,7 +122,8 @@ __global__ void band_optics_kernel(AttList a, const double* __restrict__ dz, lon
     }
     const double ext = prop[i * nprop_out];
     prop[i * nprop_out] = __dmul_rn(ext, dz[lyr]);
-    if (nprop_out > 1) prop[i * nprop_out + 1] = __ddiv_rn(prop[i * nprop_out + 1], ext);
+    // a layer without any extinction (conc = 0 aloft) has no scatterers either: ssa = 0, not 0/0
+    if (nprop_out > 1) prop[i * nprop_out + 1] = (ext == 0.0) ? 0.0 : __ddiv_rn(prop[i * nprop_out + 1], ext);
   }
 }
 
@@ -196,14 +144,6 @@ static int launch_interpn(int nval, unsigned grid, cudaStream_t st, const double
     default: return 1;
   }
   return cudaGetLastError() == cudaSuccess ? 0 : 2;
-}
-
-static Dims make_dims(const int64_t* dims, int ndim, int nval) {
-  Dims d{};
-  long off = 0, stride = nval;
-  for (int k = ndim - 1; k >= 0; --k) { d.stride[k] = stride; stride *= dims[k]; }
-  for (int k = 0; k < ndim; ++k) { d.len[k] = dims[k]; d.axis_off[k] = off; off += dims[k]; }
-  return d;
 }
 
 }  // namespace b200

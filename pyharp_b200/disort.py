@@ -288,6 +288,42 @@ class Disort:
         if rc != _cabi.OK:
             raise RuntimeError(f"b200disort_solve failed: {_cabi.strerror(rc)}")
 
+    def forward_band(self, prop, bc, temf, weights, check=True):
+        """Solve + band integration in one kernel (b200disort_solve_band): bflx (ncol, nlyr+1, 2) =
+        sum_n weights[n] F_n (examples/amars_lw.cpp:84-88) without ever writing the per-spectral-point fluxes.
+        CUDA tensors only."""
+        self._check_shapes(prop, bc, temf)
+        if not prop.is_cuda:
+            raise RuntimeError("forward_band: CUDA tensors required (use RadiationBand for host inputs)")
+        nw, nc = self.options.nwave(), self.options.ncol()
+        prop = prop.contiguous()
+        bcs = _cabi.BC()
+        keep = [prop]
+        for k, v in (bc or {}).items():
+            v = v.to(device=self.device, dtype=torch.float64).contiguous()
+            keep.append(v)
+            setattr(bcs, k, v.data_ptr())
+        tptr = None
+        if temf is not None:
+            temf = temf.to(device=self.device, dtype=torch.float64).contiguous()
+            keep.append(temf)
+            tptr = temf.data_ptr()
+        w = weights.to(device=self.device, dtype=torch.float64).contiguous()
+        bflx = torch.empty((nc, self.options.ds().nlyr + 1, 2), dtype=torch.float64, device=self.device)
+        status = torch.empty((nw, nc), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self._lib.b200disort_solve_band(self._h, prop.data_ptr(), prop.shape[3], C.byref(bcs), tptr, w.data_ptr(),
+                                                 bflx.data_ptr(), status.data_ptr())
+            if rc == _cabi.OK and check:
+                nbad = C.c_int(0)
+                rc = self._lib.b200disort_check_status(self._h, status.data_ptr(), C.byref(nbad))
+        self._status = status
+        if rc == _cabi.ERR_SOLVE:
+            raise RuntimeError(f"disort: {int((status != 0).sum())} of {nw * nc} solves failed")
+        if rc != _cabi.OK:
+            raise RuntimeError(f"b200disort_solve_band failed: {_cabi.strerror(rc)}")
+        return bflx
+
     def get_rad(self, options=None):
         """Intensities of the last forward(), shape (nwave, ncol, nphi, ntau, numu): cdisort's `uu` memory order
         (numu fastest) behind the (wave, column) batch axes.  pyharp only prints this tensor

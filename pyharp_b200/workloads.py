@@ -179,3 +179,102 @@ def make(name, nwave=None, ncol=None, nlyr=None, variant=0):
         return Workload(name, nstr, "lamber,quiet,onlyfl", prop, bc)
 
     raise KeyError(name)
+
+
+# ---------------------------------------------------------------------------------------------
+# Band-level workloads: the inputs of RadiationBand.forward (conc / pres / temp + tables) rather than
+# the optical properties, so that the opacity kernels are on the measured path too.
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class BandWorkload:
+    name: str
+    nstr: int
+    flag_tokens: str
+    nwave: int
+    tables: list            # per attenuator: dict(kind="rfm", species_id, kaxis, kdata, krefatm)
+    conc: np.ndarray        # (ncol, nlyr, nspecies) mol/m^3, layer 0 = surface
+    pres: np.ndarray        # (ncol, nlyr) Pa
+    temp: np.ndarray        # (ncol, nlyr) K
+    dz: np.ndarray          # (nlyr) m
+    bc: dict                # name -> (ncol): shared by all spectral points of the band
+    weights: np.ndarray     # (nwave)
+    wave_lower: np.ndarray = None
+    wave_upper: np.ndarray = None
+
+    @property
+    def ncol(self):
+        return self.conc.shape[0]
+
+    @property
+    def nlyr(self):
+        return self.conc.shape[1]
+
+    @property
+    def nsolve(self):
+        return self.nwave * self.ncol
+
+    def bc_full(self):
+        """The boundary fields in pydisort's (nwave, ncol) shape."""
+        return {k: np.ascontiguousarray(np.broadcast_to(v[None, :], (self.nwave, self.ncol))) for k, v in self.bc.items()}
+
+    def h2d_bytes(self):
+        return self.conc.nbytes + self.pres.nbytes + self.temp.nbytes + self.dz.nbytes + sum(v.nbytes for v in self.bc.values())
+
+
+def make_band(name="amars_lw", nwave=None, ncol=None, nlyr=None, variant=0):
+    """amars_lw as a band (examples/amars_lw.cpp:40-88 with a real atmosphere instead of its constants): two RFM
+    correlated-k attenuators (CO2, H2O) on one synthetic table file (`amarsw-ck-B1.nc` is absent from the reference
+    tree), nstr = 8, thermal emission in [1, 150] cm^-1, Lambertian surface.  The table has npres >= nlyr rows because
+    RFM's get_reftemp reads the first nlyr entries of the reference atmosphere (src/opacity/rfm.cpp:178)."""
+    if name != "amars_lw":
+        raise KeyError(name)
+    nwave, ncol, nlyr = nwave or 32, ncol or 1, nlyr or 80
+    r = _rng("amars_lw", 50 + variant)
+    npres, ntemp = max(96, nlyr), 8
+    R = 8.314462618
+    # table axes: g-points, ln p descending from the surface up (like the layers), temperature anomaly
+    g = (np.arange(nwave) + 0.5) / nwave
+    lnp_ax = np.linspace(np.log(1.2e5), np.log(5.0), npres)
+    dT_ax = np.linspace(-70.0, 70.0, ntemp)
+    tref = np.linspace(290.0, 150.0, npres) + 5.0 * np.sin(np.linspace(0.0, 6.0, npres))
+    kaxis = np.concatenate([g, lnp_ax, dT_ax])
+    krefatm = np.stack([lnp_ax, tref])
+    tables = []
+    for sid, (lo, hi, pexp, tcoef) in enumerate(((-13.0, -1.5, 0.45, 0.012), (-9.0, 4.0, 0.3, 0.02))):
+        base = lo + (hi - lo) * g ** 1.5
+        kd = (base[:, None, None] + pexp * (lnp_ax[None, :, None] - np.log(1.0e5)) + tcoef * dT_ax[None, None, :]
+              + 0.05 * r.standard_normal((nwave, npres, ntemp)))
+        tables.append(dict(kind="rfm", species_id=sid, kaxis=kaxis, kdata=np.ascontiguousarray(kd), krefatm=krefatm))
+    # atmosphere: hydrostatic-like pressure, lapse-rate temperature with a per-column offset (index 0 = surface)
+    z = (np.arange(nlyr) + 0.5) / nlyr
+    p0 = 1.0e5 * (1.0 + 0.05 * r.uniform(-1.0, 1.0, (ncol, 1)))
+    pres = p0 * np.exp(-7.5 * z[None, :])
+    temp = 295.0 - 140.0 * z[None, :] + r.uniform(-6.0, 6.0, (ncol, 1)) + 1.5 * r.standard_normal((ncol, nlyr))
+    ntot = pres / (R * temp)
+    q = 10.0 ** r.uniform(-4.0, -2.5, (ncol, 1)) * np.exp(-3.0 * z[None, :])
+    conc = np.stack([0.95 * ntot, q * ntot], axis=-1)
+    dz = np.full(nlyr, 60.0e3 / nlyr)
+    tsurf = temp[:, 0] + 2.0
+    bc = {"albedo": r.uniform(0.0, 0.3, ncol) if variant else np.zeros(ncol), "btemp": tsurf}
+    w = r.uniform(0.5, 1.5, nwave)
+    return BandWorkload(name, 8, "lamber,quiet,onlyfl,planck", nwave, tables, np.ascontiguousarray(conc),
+                        np.ascontiguousarray(pres), np.ascontiguousarray(temp), dz, bc, w / w.sum(),
+                        np.full(nwave, 1.0), np.full(nwave, 150.0))
+
+
+def band_of(bw, ncol=None, exact_interp=False, mix_eps=0.0, device=None):
+    """pyharp_b200.RadiationBand for a BandWorkload."""
+    from .band import RadiationBand, RadiationBandOptions
+    from .disort import DisortOptions
+    from .opacity import AttenuatorOptions, RFM
+    atts = {}
+    for k, t in enumerate(bw.tables):
+        op = AttenuatorOptions().species_ids([t["species_id"]]).species_names(["CO2", "H2O"]).type("rfm")
+        atts[f"a{k}"] = RFM(op, t["kaxis"], t["kdata"], t["krefatm"], device=device or "cuda")
+    dop = DisortOptions().flags(bw.flag_tokens)
+    d = dop.ds()
+    d.nstr = d.nmom = bw.nstr
+    bo = (RadiationBandOptions().attenuators(atts).disort(dop).nlyr(bw.nlyr).ncol(ncol or bw.ncol)
+          .wave_lower(list(bw.wave_lower)).wave_upper(list(bw.wave_upper)).weights(bw.weights)
+          .exact_interp(exact_interp).mix_eps(mix_eps))
+    return RadiationBand(bo, device=device, nspecies=bw.conc.shape[2])

@@ -27,11 +27,20 @@ static void run(SolveParams& p, const QuadTables& qt) {
   unsigned ring_pos = 0;  // (device only: position in the warp's shared-memory ring of back-sweep records)
   BackPend<NN> pend;
   int it = 0;
-  for (long s = 0; s < nsolve; ++s, ++it) {
-    if (p.nprop <= 2 && NN <= 4) solve_flux_one<NN, true>(p, qt, s, 0, true, ring_pos, pend, it & 1);  // same dispatch as flux_inst.cu
-    else solve_flux_one<NN, false>(p, qt, s, 0, true, ring_pos, pend, it & 1);
+  const bool band = p.bflx_t != nullptr;  // fused band integration (SolveParams::bflx_t)
+  for (long s = 0; s < nsolve; ++s, ++it) {  // same dispatch as flux_inst.cu
+    if (p.nprop <= 2 && NN <= 4) {
+      if (band) solve_flux_one<NN, true, 1>(p, qt, s, 0, true, ring_pos, pend, it & 1);
+      else solve_flux_one<NN, true, 0>(p, qt, s, 0, true, ring_pos, pend, it & 1);
+    } else {
+      if (band) solve_flux_one<NN, false, 1>(p, qt, s, 0, true, ring_pos, pend, it & 1);
+      else solve_flux_one<NN, false, 0>(p, qt, s, 0, true, ring_pos, pend, it & 1);
+    }
   }
-  if constexpr (kCarryBack<NN>) drain_back_sweep<NN>(pend, qt, 0, ring_pos);
+  if constexpr (kCarryBack<NN>) {
+    if (band) drain_back_sweep<NN, 1>(p, pend, qt, 0, ring_pos);
+    else drain_back_sweep<NN, 0>(p, pend, qt, 0, ring_pos);
+  }
 }
 
 extern "C" int hostsim_flux(int nwave, int ncol, int nlyr, int nstr, int nprop, unsigned flags,
@@ -39,10 +48,11 @@ extern "C" int hostsim_flux(int nwave, int ncol, int nlyr, int nstr, int nprop, 
                             const double* albedo, const double* btemp, const double* ttemp,
                             const double* temis, const double* fisot, const double* temf,
                             const double* wave_lower, const double* wave_upper, double* flx,
-                            int* status) {
+                            int* status, const double* weights, double* bflx_t, int bc_bcast) {
   QuadTables qt;
   build_quad_tables(nstr, &qt);
   SolveParams p{};
+  p.weights = weights; p.bflx_t = bflx_t; p.bc_bcast = bc_bcast;  // band mode when bflx_t != NULL (zeroed by the caller)
   p.nwave = nwave; p.ncol = ncol; p.nlyr = nlyr; p.nprop = nprop; p.nstr = nstr; p.flags = flags;
   p.prop = prop; p.umu0 = umu0; p.fbeam = fbeam; p.albedo = albedo; p.btemp = btemp;
   p.ttemp = ttemp; p.temis = temis; p.fisot = fisot; p.flx = flx; p.status = status;

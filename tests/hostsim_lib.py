@@ -22,7 +22,7 @@ def _lib():
     lib = C.CDLL(so)
     dp = C.POINTER(C.c_double)
     lib.hostsim_flux.restype = C.c_int
-    lib.hostsim_flux.argtypes = [C.c_int] * 5 + [C.c_uint] + [dp] * 12 + [C.POINTER(C.c_int)]
+    lib.hostsim_flux.argtypes = [C.c_int] * 5 + [C.c_uint] + [dp] * 12 + [C.POINTER(C.c_int), dp, dp, C.c_int]
     lib.hostsim_intensity.restype = C.c_int
     lib.hostsim_intensity.argtypes = ([C.c_int] * 6 + [C.c_uint, C.c_double] + [C.c_int] * 3 + [dp] * 17
                                       + [C.POINTER(C.c_int)])
@@ -32,7 +32,9 @@ def _lib():
 _L = None
 
 
-def flux(prop, bc=None, temf=None, *, nstr, flags, wave_lower=None, wave_upper=None):
+def flux(prop, bc=None, temf=None, *, nstr, flags, wave_lower=None, wave_upper=None, weights=None, bc_bcast=False):
+    """Flux kernel body on the host.  With `weights` (nwave) the BAND instantiation runs instead (fused band
+    integration): returns (bflx (ncol, nlyr+1, 2), status).  bc_bcast: boundary fields are (ncol) arrays."""
     global _L
     if _L is None:
         _L = _lib()
@@ -54,13 +56,17 @@ def flux(prop, bc=None, temf=None, *, nstr, flags, wave_lower=None, wave_upper=N
     bc = bc or {}
     flx = np.zeros((nwave, ncol, nlyr + 1, 2))
     st = np.zeros((nwave, ncol), dtype=np.int32)
-    sh = (nwave, ncol)
+    sh = (ncol,) if bc_bcast else (nwave, ncol)
+    bflx_t = None if weights is None else np.zeros((nlyr + 1, 2, ncol))
     rc = _L.hostsim_flux(nwave, ncol, nlyr, nstr, nprop, flags, P(prop),
                          P(bc.get("umu0"), sh), P(bc.get("fbeam"), sh), P(bc.get("albedo"), sh),
                          P(bc.get("btemp"), sh), P(bc.get("ttemp"), sh), P(bc.get("temis"), sh),
                          P(bc.get("fisot"), sh), P(temf), P(wave_lower), P(wave_upper),
-                         flx.ctypes.data_as(dp), st.ctypes.data_as(C.POINTER(C.c_int)))
+                         flx.ctypes.data_as(dp), st.ctypes.data_as(C.POINTER(C.c_int)), P(weights),
+                         None if bflx_t is None else bflx_t.ctypes.data_as(dp), int(bc_bcast))
     assert rc == 0
+    if bflx_t is not None:
+        return np.ascontiguousarray(bflx_t.transpose(2, 0, 1)), st
     return flx, st
 
 

@@ -28,6 +28,10 @@ def test_header_symbols_exported():
     assert len(onames) == 7 and sorted(_cabi.OPACITY_EXPORTS) == onames
     for n in onames:
         assert hasattr(lib, n), f"{n} declared in include/b200opacity.h but not exported"
+    bnames = sorted(declared_functions("b200band.h", "b200_band_") + declared_functions("b200band.h", "b200disort_"))
+    assert len(bnames) == 11 and sorted(_cabi.BAND_EXPORTS) == bnames
+    for n in bnames:
+        assert hasattr(lib, n), f"{n} declared in include/b200band.h but not exported"
 
 
 def test_flag_values_match_header():
@@ -61,6 +65,41 @@ def test_no_cpu_fallback():
     from pyharp_b200 import Disort, DisortOptions
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         Disort(DisortOptions().flags("lamber,onlyfl"))
+
+
+def test_band_structs_match_header():
+    """ctypes mirrors of b200_attenuator / b200_band_config / b200_band_io: field order and sizes as a C compiler
+    lays them out (compiled here with gcc from the header itself)."""
+    import subprocess
+    import tempfile
+    src = r"""
+#include <stdio.h>
+#include <stddef.h>
+#include "b200band.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(b200_attenuator), sizeof(b200_band_config), sizeof(b200_band_io),
+         offsetof(b200_attenuator, kwave), offsetof(b200_band_config, mix_eps), offsetof(b200_band_io, bflx),
+         offsetof(b200_band_io, prop), offsetof(b200_band_config, weights));
+  return 0;
+}
+"""
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
+        got = [int(x) for x in subprocess.check_output([os.path.join(d, "t")]).split()]
+    want = [C.sizeof(_cabi.Attenuator), C.sizeof(_cabi.BandConfig), C.sizeof(_cabi.BandIO), _cabi.Attenuator.kwave.offset,
+            _cabi.BandConfig.mix_eps.offset, _cabi.BandIO.bflx.offset, _cabi.BandIO.prop.offset, _cabi.BandConfig.weights.offset]
+    assert got == want
+
+
+def test_band_create_rejects_bad_config():
+    lib = _cabi.lib()
+    h = C.c_void_p()
+    cfg = _cabi.BandConfig()
+    assert lib.b200_band_create(None, C.byref(h)) == _cabi.ERR_INVALID
+    assert lib.b200_band_create(C.byref(cfg), C.byref(h)) == _cabi.ERR_INVALID      # no attenuators
+    assert lib.b200_band_forward(None, None) == _cabi.ERR_INVALID
+    assert lib.b200_band_allreduce(None, None, 0, None) == _cabi.ERR_INVALID
 
 
 def test_create_rejects_bad_config():
