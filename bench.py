@@ -1,23 +1,38 @@
 #!/usr/bin/env python
 """bench.py -- DISORT solves/s on B200 (BASELINE.json metric), one process per GPU.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload amars_lw|amars_sw|lbl|gcm]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload amars_lw|amars_sw|lbl|gcm] [--shard col|wave]
   python bench.py --impl reference ...      # the CPU path (oracle restatement of cdisort) on host cores
 
-A "step" is one pass of the hot path over one batch of synthetic atmospheres: the Planck pre-pass
-(when thermal), the DISORT flux-solve kernel over every (g-point, column) of the batch and the
-weighted band integration.  The default workload is the one the metric is quoted on: amars_lw
-shape, nstr = 8, 80 layers, correlated-k g-points x columns, thermal emission.  Columns are sharded
-over ranks (weak scaling: fixed columns per GPU); the band integration is then rank-local and no
-collective is on the data path.
+Default workload = the configuration the metric is quoted on: amars_lw shape (nstr = 8, 80 layers, 32 correlated-k
+g-points x 16384 columns per GPU, thermal emission), driven the way pyharp drives it -- as a radiation BAND
+(src/radiation/radiation_band.cpp:75-128, examples/amars_lw.cpp:62-88): a "step" is one pass of the per-band hot
+path over one batch of synthetic atmospheres,
 
-Reported: `value` = solves/s with inputs resident in HBM (CUDA events, max over ranks);
-`e2e` = the same through Disort.forward() with HOST tensors (pinned), H2D and D2H inside the timed
-region; `roofline` = algorithmic FP64 flops (reference-algorithm count W) per launch
-/ measured kernel duration against the measured DFMA peak, with the HBM view beside it;
-`cpu_baseline` = the oracle on the host cores on a bounded sample.
+    conc / pres / temp -> RFM correlated-k optics -> layer2level + Planck pre-pass -> DISORT flux solve of every
+    (g-point, column) -> band integration sum_g w_g F_g (fused into the solve kernel's flux epilogue)
+
+through ONE C-ABI call (include/b200band.h).  Columns are sharded over ranks (weak scaling: fixed columns per GPU);
+the band integration is then rank-local and no collective is on the data path.
+
+  value      solves/s with the band's inputs resident in HBM (b200_band_forward; CUDA events, max over ranks)
+  e2e        the same call with HOST tensors (b200_band_forward_host): H2D of conc / pres / temp / boundary fields and
+             D2H of the (ncol, nlyr+1, 2) band flux inside the timed region
+  kernel     the flux-solve kernel alone (events around each launch, b200disort_get_stats)
+  roofline   that kernel against the measured FP64 (DFMA) peak: `frac` = executed FP64 flops (ncu count per solve of the
+             committed capture of exactly these sources, profiles/r02/traffic.json) x this run's rate / peak;
+             `algorithmic_equiv` = the reference algorithm's flop count W at this rate, for comparison
+  other_workloads   BASELINE.json configs 2, 4, 5 (amars_sw, line-by-line, full-size GCM batch) on the same box
+  opacity    the optics kernels against the HBM copy peak
+  cpu_baseline  the oracle on the host cores on a bounded sample
+
+`--workload X` (X != amars_lw) measures the solver-level step of that shape instead (prop resident in HBM ->
+Planck pre-pass -> solve + fused band integration; e2e through Disort.forward with host tensors);
+`--workload lbl --shard wave` is the spectral-point sharding of BASELINE config 4: 10^5 wavenumbers x 1 column
+split over the ranks (strong scaling), one NCCL all-reduce of the band flux per step (b200disort_allreduce_band).
 """
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -30,9 +45,13 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 METRIC = "DISORT solves/sec (nstr=8, 80 layers)"
-DEFAULT_COLS = {"amars_lw": 16384, "amars_sw": 1024, "lbl": 8, "gcm": 2048}
+DEFAULT_COLS = {"amars_lw": 16384, "amars_sw": 1024, "lbl": 8, "gcm": 65536}
 DEFAULT_NWAVE = {"amars_lw": 32, "amars_sw": 500, "lbl": 100000, "gcm": 32}
 DEFAULT_NLYR = {"amars_lw": 80, "amars_sw": 40, "lbl": 40, "gcm": 60}
+GCM_SEED_COLS = 2048  # the full-size GCM batch tiles a seeded block of this many columns (18 GB of inputs)
+TRAFFIC = os.path.join(ROOT, "profiles", "r02", "traffic.json")
+HASHED = ["pyharp_b200/csrc/disort_solver_body.inc", "pyharp_b200/csrc/disort_device.cuh",
+          "pyharp_b200/csrc/flux_inst.cu", "pyharp_b200/workloads.py"]
 
 
 def parse():
@@ -42,29 +61,41 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="amars_lw", choices=sorted(DEFAULT_COLS))
+    ap.add_argument("--shard", default="col", choices=["col", "wave"])
     ap.add_argument("--ncol", type=int, default=0, help="columns per GPU")
     ap.add_argument("--nwave", type=int, default=0)
     ap.add_argument("--nlyr", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0, help="solves in the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip other_workloads / opacity")
+    ap.add_argument("--prop-level", action="store_true", help="amars_lw through the solver-level entry (round-1 step)")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the process to the GPU's NUMA node")
     return ap.parse_args()
 
 
-def shape_of(args):
-    name = args.workload
+def shape_of(args, name=None):
+    name = name or args.workload
     return (args.nwave or DEFAULT_NWAVE[name], args.ncol or DEFAULT_COLS[name], args.nlyr or DEFAULT_NLYR[name])
 
 
-def config_of(args, wl, world):
-    nwave, ncol, nlyr, nprop = wl.shape
-    return {"workload": f"{args.workload}-shape synthetic: {nwave} spectral points x {ncol} columns per GPU x "
-                        f"{nlyr} layers, nstr={wl.nstr}, nprop={nprop}, flags={wl.flag_tokens}",
-            "solves_per_step_per_gpu": wl.nsolve, "nstr": wl.nstr, "nlyr": nlyr, "nwave": nwave,
-            "ncol_per_gpu": ncol, "sharding": f"columns x{world}, no data-path collective",
-            "l2": "inputs (%.0f MB) and back-sweep workspace exceed the 126 MB L2; no explicit flush"
-                  % (wl.prop.nbytes / 1e6),
-            "flops_per_solve_W": wl.flops_per_solve(), "bytes_per_solve_Q": wl.bytes_per_solve()}
+def kernel_hash():
+    h = hashlib.sha256()
+    for f in HASHED:
+        h.update(open(os.path.join(ROOT, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def traffic_entry(name):
+    """ncu counters per solve of the solve kernel for this workload -- only if the committed capture was taken
+    with exactly the current kernel sources and workload generator."""
+    try:
+        tr = json.load(open(TRAFFIC))
+    except Exception:  # noqa: BLE001
+        return None, "no capture"
+    if tr.get("hash") != kernel_hash():
+        return None, "stale"
+    return tr.get(name), None
 
 
 # ---------------------------------------------------------------------------------------------
@@ -72,7 +103,7 @@ def config_of(args, wl, world):
 # ---------------------------------------------------------------------------------------------
 def cpu_sample(args, wl_name, nsolve_target):
     from pyharp_b200 import workloads as W
-    nwave, _, nlyr = shape_of(args)
+    nwave, _, nlyr = shape_of(args, wl_name)
     nw = min(nwave, 32)
     ncol = max(1, nsolve_target // nw)
     return W.make(wl_name, nwave=nw, ncol=ncol, nlyr=nlyr, variant=7)
@@ -103,7 +134,8 @@ def cpu_baseline(args):
     return {"value": wl.nsolve / dt, "unit": "solves/s", "cores": cores, "kind": "port",
             "sample": f"{wl.nsolve} solves of the same workload shape ({wl.shape[0]} spectral points x {wl.shape[1]} "
                       f"columns x {wl.shape[2]} layers) in {dt:.2f} s, OpenMP over solves; oracle/ restatement of "
-                      f"cdisort (cdisort itself is un-vendored in the reference)"}
+                      f"cdisort's DISORT solve (cdisort itself is un-vendored in the reference); the opacity stage of "
+                      f"the GPU step is not in the CPU sample"}
 
 
 def run_reference(args):
@@ -130,7 +162,8 @@ def run_reference(args):
     sample = (f"each step = {wl.nsolve} solves ({wl.shape[0]} x {wl.shape[1]} columns x {wl.shape[2]} layers) of the "
               f"workload, OpenMP over solves on {cores} threads")
     out = {"metric": METRIC, "value": v, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+           "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+           "scaling": "strong" if args.shard == "wave" else "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
            "config": {"workload": f"{args.workload}-shape synthetic: {nwave} spectral points x {ncol} columns per GPU "
                                   f"x {nlyr} layers, nstr={full.nstr} (CPU arm: bounded sample per step)",
@@ -177,6 +210,8 @@ class Clocks:
 
     def start(self):
         if self.N:
+            self.samples, self.reasons = [], set()
+            self._stop.clear()
             self._th = threading.Thread(target=self._loop, daemon=True)
             self._th.start()
 
@@ -184,11 +219,188 @@ class Clocks:
         if self._th:
             self._stop.set()
             self._th.join()
+            self._th = None
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": getattr(self, "err", "no samples")}
         idle = {"GpuIdle", "ApplicationsClocksSetting"}
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(r for r in self.reasons if r not in idle), "samples": len(self.samples)}
+
+
+def bind_numa(local):
+    """Pin this process to the CPUs NVML reports as local to its GPU, BEFORE any pinned host memory is allocated, so
+    that the staging memory of every rank sits on the NUMA node of its GPU's PCIe root (round 1: all ranks on node 0
+    saturated at ~117 GB/s box-wide)."""
+    try:
+        import pynvml as N
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        words = N.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1 and 64 * i + b < ncpu}
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(cpus & allowed)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"cpus": f"{cpus[0]}-{cpus[-1]}" if cpus == list(range(cpus[0], cpus[-1] + 1)) else len(cpus),
+                    "n": len(cpus)}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
+    return {"n": 0}
+
+
+# ---------------------------------------------------------------------------------------------
+class Ctx:
+    pass
+
+
+def timed_region(ctx, fn, steps):
+    """`steps` calls of fn between barrier + synchronize; CUDA events on the current stream; max over ranks."""
+    import torch
+    import torch.distributed as dist
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if ctx.world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    if ctx.world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=ctx.dev)
+    if ctx.world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return ms, float(t.item())
+
+
+def wall_region(ctx, fn, steps):
+    """Host-timed region for calls that synchronise themselves (host-pointer entries); max over ranks."""
+    import torch
+    import torch.distributed as dist
+    if ctx.world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=ctx.dev)
+    if ctx.world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def roofline_of(name, W_, Q_, nsolve, kernel_ms, fp64_peak, hbm_peak, hbm_src):
+    """Roofline record of the solve kernel: executed FP64 flops (ncu, committed capture of these sources) against the
+    measured DFMA peak; the reference-algorithm count W beside it; DRAM traffic against the HBM copy peak."""
+    tr, why = traffic_entry(name)
+    sec = kernel_ms * 1e-3
+    r = {"bound": "fp64", "unit": "TFLOP/s", "peak": fp64_peak,
+         "peak_source": "DFMA-saturating kernel measured in this run (b200disort_fp64_peak)",
+         "algorithmic_equiv": {"flop_per_solve_W": W_, "tflops": W_ * nsolve / sec / 1e12,
+                               "frac": W_ * nsolve / sec / 1e12 / fp64_peak,
+                               "note": "reference-algorithm (banded LU + QR) flop count of SURVEY.md 8d at this rate; the "
+                                       "adding-method kernel executes about a third of it, so this can exceed 1"},
+         "hbm": {"algorithmic_bytes_per_solve_Q": Q_, "algorithmic_gbs": Q_ * nsolve / sec / 1e9, "peak": hbm_peak,
+                 "peak_source": hbm_src}}
+    if tr is None:
+        r.update({"achieved": None, "frac": None, "traffic": None, "executed": None, "stale": why == "stale",
+                  "note": f"no ncu capture of the current kernel sources ({why}); see profiles/r02"})
+        return r
+    ex = tr["executed_flop_per_solve"] * nsolve / sec / 1e12
+    traffic = tr["bytes_per_launch"] / tr["solves_per_launch"] * nsolve
+    r.update({"achieved": ex, "frac": ex / fp64_peak, "traffic": traffic, "stale": False,
+              "executed": {"flop_per_solve": tr["executed_flop_per_solve"], "fp64_pipe_active_pct_ncu": tr["fp64_pipe_active_pct"],
+                           "source": tr.get("capture")},
+              "note": "achieved = FP64 flops the kernel executes per solve (ncu DFMA x 2 + DMUL + DADD of the committed "
+                      "capture, hash-checked against the current sources) x solves per launch / measured launch duration"})
+    r["hbm"].update({"traffic_bytes_per_solve": traffic / nsolve, "dram_gbs": traffic / sec / 1e9,
+                     "dram_frac_of_hbm_peak": traffic / sec / 1e9 / hbm_peak,
+                     "traffic_over_algorithmic": traffic / nsolve / Q_})
+    return r
+
+
+def peaks():
+    p = {}
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    return (p["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in p else (6650.0, "fallback (B200_PROFILING.md)")
+
+
+# ---------------------------------------------------------------------------------------------
+# solver-level step of a named workload: prop in HBM -> Planck pre-pass -> solve + fused band integration
+# ---------------------------------------------------------------------------------------------
+def solver_step_bench(ctx, name, nwave, ncol, nlyr, steps, warmup, variant=0, tile=1, e2e_steps=0):
+    import torch
+    from pyharp_b200 import Disort, workloads as W
+    dev = ctx.dev
+    wl = W.make(name, nwave=nwave, ncol=ncol // tile, nlyr=nlyr, variant=variant)
+    to_dev = lambda a: None if a is None else torch.from_numpy(a).to(dev)
+    rep = lambda t, dim: t if (t is None or tile == 1) else t.repeat(*[tile if i == dim else 1 for i in range(t.dim())])
+    d_prop = rep(to_dev(wl.prop), 1)
+    d_bc = {k: rep(to_dev(v), 1) for k, v in wl.bc.items()}
+    d_temf = rep(to_dev(wl.temf), 0)
+    op = wl.options().ncol(ncol)
+    ds = Disort(op)
+    weights = torch.full((nwave,), 1.0 / nwave, dtype=torch.float64, device=dev)
+    step = lambda: ds.forward_band(d_prop, d_bc, d_temf, weights, check=False)
+    for _ in range(max(warmup, 3)):
+        bflx = step()
+    torch.cuda.synchronize()
+    assert int(ds.status().abs().sum()) == 0, f"non-zero solve status in the {name} workload"
+    assert bool(torch.isfinite(bflx).all())
+    ds.stats()
+    ctx.clocks.start()
+    ms, ms_max = timed_region(ctx, step, steps)
+    clk = ctx.clocks.stop()
+    st = ds.stats()
+    kernel_ms = st["solve_kernel_ms"] / max(1, st["solves_timed"])
+    nsolve = nwave * ncol
+    out = {"nsolve": nsolve, "ms": ms, "ms_max": ms_max, "kernel_ms": kernel_ms, "clocks": clk, "wl": wl, "ds": ds,
+           "launches_per_step": 2 + (1 if wl.thermal else 0), "workspace_bytes": st["workspace_bytes"], "nprop": wl.shape[3],
+           "prop_bytes": d_prop.numel() * 8}
+    if e2e_steps:
+        h_prop = torch.from_numpy(wl.prop).pin_memory()
+        h_bc = {k: torch.from_numpy(v).pin_memory() for k, v in wl.bc.items()}
+        h_temf = None if wl.temf is None else torch.from_numpy(wl.temf).pin_memory()
+        ds1 = ds if tile == 1 else Disort(wl.options())
+        for _ in range(2):
+            flx = ds1.forward(h_prop, h_bc, h_temf)
+        dt = wall_region(ctx, lambda: ds1.forward(h_prop, h_bc, h_temf), e2e_steps)
+        out["e2e"] = {"value": wl.nsolve * ctx.world * e2e_steps / dt, "unit": "solves/s",
+                      "h2d_bytes_per_step": int(h_prop.nbytes + sum(v.nbytes for v in h_bc.values()) + (0 if h_temf is None else h_temf.nbytes)),
+                      "d2h_bytes_per_step": int(flx.nbytes + wl.nsolve * 4), "steps": e2e_steps,
+                      "api": "pyharp_b200.Disort.forward(host tensors) -> b200disort_solve_host (per-spectral-point fluxes out)"}
+    return out
+
+
+def nccl_selfcheck(ctx):
+    """Spectral-point sharding on a small line-by-line shaped problem: every rank solves its slice of the spectral
+    points with the fused band integration, the C-ABI all-reduce (b200disort_allreduce_band on a raw ncclComm_t)
+    finishes the band flux, and the result must equal the single-GPU band flux each rank computes by itself."""
+    import torch
+    from pyharp_b200 import Disort, shard as S, workloads as W
+    nw = 64 * ctx.world
+    wl = W.make("lbl", nwave=nw, ncol=1, nlyr=12, variant=3)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(ctx.dev)
+    w = torch.linspace(0.5, 1.5, nw, dtype=torch.float64, device=ctx.dev)
+    whole = Disort(wl.options()).forward_band(t(wl.prop), {k: t(v) for k, v in wl.bc.items()}, None, w)
+    sh = S.Shard("wave", *S._split(nw, ctx.world, ctx.rank), ctx.world, ctx.rank)
+    prop, bc, _, ww, _, _ = S.take(sh, wl.prop, wl.bc, None, w)
+    ds = Disort(wl.options().nwave(sh.size))
+    part = ds.forward_band(t(prop), {k: t(v) for k, v in bc.items()}, None, ww)
+    ds.allreduce_band(part, ctx.comm)
+    torch.cuda.synchronize()
+    err = float((part - whole).abs().max() / whole.abs().max())
+    assert err < 1e-12, f"NCCL band-flux all-reduce mismatch: {err}"
+    return {"ok": True, "max_rel_err": err, "ranks": ctx.world, "nccl_version": ctx.comm.version,
+            "what": "spectral-point sharding + b200disort_allreduce_band == single-GPU band flux"}
 
 
 def main():
@@ -197,150 +409,250 @@ def main():
         run_reference(args)
         return
 
-    import ctypes as C
     import torch
     import torch.distributed as dist
-    from pyharp_b200 import Disort, fp64_peak_tflops, workloads as W, _cabi
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference)")
+    numa = None if args.no_numa else bind_numa(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    nwave, ncol, nlyr = shape_of(args)
-    wl = W.make(args.workload, nwave=nwave, ncol=ncol, nlyr=nlyr, variant=rank)
-    ds = Disort(wl.options())
-    weights = torch.full((nwave,), 1.0 / nwave, dtype=torch.float64, device=dev)
-
-    # ---- device-resident leg
-    to_dev = lambda a: None if a is None else torch.from_numpy(a).to(dev)
-    d_prop = to_dev(wl.prop)
-    d_bc = {k: to_dev(v) for k, v in wl.bc.items()}
-    d_temf = to_dev(wl.temf)
-    bcs = _cabi.BC()
-    for k, v in d_bc.items():
-        setattr(bcs, k, v.data_ptr())
-    d_flx = torch.empty((nwave, ncol, nlyr + 1, 2), dtype=torch.float64, device=dev)
-    d_status = torch.empty((nwave, ncol), dtype=torch.int32, device=dev)
-    tptr = None if d_temf is None else d_temf.data_ptr()
-
-    def step_device():
-        ds.forward_device_async(d_prop, bcs, tptr, d_flx, d_status)
-        return ds.reduce_band(d_flx, weights)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        bflx = step_device()
-    torch.cuda.synchronize()
-    assert int(d_status.abs().sum()) == 0, "non-zero solve status in the bench workload"
-    assert bool(torch.isfinite(bflx).all())
-    ds.stats()  # reset the kernel-time accumulator
-    launches_per_step = 2 + (1 if wl.thermal else 0)  # planck pre-pass, flux solve, band reduction
-
-    clocks = Clocks(local)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    clocks.start()
-    e0.record()
-    for _ in range(args.steps):
-        step_device()
-    e1.record()
-    barrier()
-    clk = clocks.stop()
-    ms = e0.elapsed_time(e1)
-    st = ds.stats()
-    kernel_ms = st["solve_kernel_ms"] / max(1, st["solves_timed"])
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    from pyharp_b200 import fp64_peak_tflops, workloads as W
+    ctx = Ctx()
+    ctx.rank, ctx.world, ctx.local, ctx.dev = rank, world, local, dev
+    ctx.clocks = Clocks(local)
+    ctx.comm = None
+    nccl_check = None
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = wl.nsolve * world * args.steps / (ms_max * 1e-3)
+        from pyharp_b200.nccl import Communicator
+        ctx.comm = Communicator(local)
+        nccl_check = nccl_selfcheck(ctx)
+    hbm_peak, hbm_src = peaks()
+    steps, warmup = args.steps, max(args.warmup, 3)
+    nwave, ncol, nlyr = shape_of(args)
+    out = None
 
-    # ---- end-to-end leg: host (pinned) tensors through the public API
-    e2e = None
-    if not args.no_e2e:
-        h_prop = torch.from_numpy(wl.prop).pin_memory()
-        h_bc = {k: torch.from_numpy(v).pin_memory() for k, v in wl.bc.items()}
-        h_temf = None if wl.temf is None else torch.from_numpy(wl.temf).pin_memory()
-        h2d = h_prop.nbytes + sum(v.nbytes for v in h_bc.values()) + (0 if h_temf is None else h_temf.nbytes)
-        flx = None
-        for _ in range(2):
-            flx = ds.forward(h_prop, h_bc, h_temf)
-        d2h = flx.nbytes + nwave * ncol * 4
-        esteps = max(3, min(args.steps, 10))
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(esteps):
-            flx = ds.forward(h_prop, h_bc, h_temf)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": wl.nsolve * world * esteps / float(t.item()), "unit": "solves/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": esteps,
-               "api": "pyharp_b200.Disort.forward(host tensors) -> b200disort_solve_host"}
-        ds.stats()
-
-    if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:  # noqa: BLE001
-            pass
-        hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
-        fp64_peak = fp64_peak_tflops(local)
-        W_, Q_ = wl.flops_per_solve(), wl.bytes_per_solve()
-        traffic, executed = None, None
-        try:  # per-solve counters of the solve kernel from the committed ncu --set full capture of this workload
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01", "traffic.json")))[args.workload]
-            traffic = tr["bytes_per_launch"] / tr["solves_per_launch"] * wl.nsolve
-            ex_tf = tr["executed_flop_per_solve"] * wl.nsolve / (kernel_ms * 1e-3) / 1e12
-            executed = {"flop_per_solve": tr["executed_flop_per_solve"], "tflops": ex_tf, "frac_of_fp64_peak": ex_tf / fp64_peak,
-                        "fp64_pipe_active_pct_ncu": tr["fp64_pipe_active_pct"],
-                        "dram_gbs": traffic / (kernel_ms * 1e-3) / 1e9,
-                        "dram_frac_of_hbm_peak": traffic / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
-                        "source": tr.get("capture", "profiles/r01")}
-        except Exception:  # noqa: BLE001
-            pass
-        ach_tf = W_ * wl.nsolve / (kernel_ms * 1e-3) / 1e12
-        ach_gbs = Q_ * wl.nsolve / (kernel_ms * 1e-3) / 1e9
-        out = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
-               "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": config_of(args, wl, world), "clocks": clk,
-               "gpu_launches": launches_per_step * args.steps,
-               "kernel": {"name": "disort_flux_kernel", "avg_ms": kernel_ms, "share_of_step": kernel_ms / (ms / args.steps),
-                          "workspace_bytes": st["workspace_bytes"]},
-               "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                            "frac": ach_tf / fp64_peak, "traffic": traffic,
-                            "peak_source": "DFMA-saturating kernel measured in this run (b200disort_fp64_peak); "
-                                           "profiles/microbench/fp64_peak_r01.json has the sweep",
-                            "executed": executed,
-                            "note": "achieved = reference-algorithm flop count W (SURVEY.md 8d) x solves / kernel time. "
-                                    "The adding-method kernel executes about a third of W, so frac can exceed 1; the "
-                                    "utilisation actually reached is in `executed`: FP64 instructions the kernel issues "
-                                    "(ncu count per solve x this run's rate) against the measured DFMA peak, and its DRAM "
-                                    "traffic (ncu bytes per solve x this run's rate; back-sweep workspace dominates) "
-                                    "against the measured HBM copy bandwidth"},
-               "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
-                                "frac": ach_gbs / hbm_peak, "peak_source": hbm_src},
-               "e2e": e2e}
+    if args.workload == "lbl" and args.shard == "wave":
+        out = bench_wave_sharded(ctx, args, nwave, nlyr, steps, warmup)
+    elif args.workload == "amars_lw" and not args.prop_level:
+        out = bench_band(ctx, args, nwave, ncol, nlyr, steps, warmup, hbm_peak, hbm_src)
+    else:
+        tile = max(1, ncol // GCM_SEED_COLS) if args.workload == "gcm" else 1
+        r = solver_step_bench(ctx, args.workload, nwave, ncol, nlyr, steps, warmup, variant=rank, tile=tile,
+                              e2e_steps=0 if args.no_e2e else max(3, min(steps, 10)))
+        if rank == 0:
+            wl = r["wl"]
+            fp64_peak = fp64_peak_tflops(local)
+            value = r["nsolve"] * world * steps / (r["ms_max"] * 1e-3)
+            out = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+                   "ms_per_step": r["ms_max"] / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                   "dtype": "f64", "data": "synthetic",
+                   "config": {"workload": f"{args.workload}-shape synthetic: {nwave} spectral points x {ncol} columns per GPU x "
+                                          f"{nlyr} layers, nstr={wl.nstr}, nprop={r['nprop']}, flags={wl.flag_tokens}"
+                                          + (f"; a seeded block of {ncol // tile} columns tiled {tile}x" if tile > 1 else ""),
+                              "step": "prop resident in HBM -> Planck pre-pass -> flux solve with fused band integration "
+                                      "(b200disort_solve_band)",
+                              "solves_per_step_per_gpu": r["nsolve"], "nstr": wl.nstr, "nlyr": nlyr, "nwave": nwave,
+                              "ncol_per_gpu": ncol, "sharding": f"columns x{world}, no data-path collective",
+                              "l2": "inputs (%.0f MB) and back-sweep workspace exceed the 126 MB L2; no explicit flush" % (r["prop_bytes"] / 1e6)},
+                   "clocks": r["clocks"], "gpu_launches": (r["launches_per_step"] + 1) * steps,
+                   "kernel": {"name": "disort_flux_kernel", "avg_ms": r["kernel_ms"], "share_of_step": r["kernel_ms"] / (r["ms"] / steps),
+                              "workspace_bytes": r["workspace_bytes"]},
+                   "roofline": roofline_of(args.workload, wl.flops_per_solve(), wl.bytes_per_solve(), r["nsolve"], r["kernel_ms"],
+                                           fp64_peak, hbm_peak, hbm_src),
+                   "e2e": r.get("e2e")}
+    if rank == 0 and out is not None:
+        if numa is not None:
+            out["numa_binding"] = numa
+        if nccl_check is not None:
+            out["nccl_band_allreduce_check"] = nccl_check
         if not args.no_cpu and world == 1:  # the CPU leg is reported at N = 1 only
             out["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
+        if ctx.comm is not None:
+            ctx.comm.destroy()
         dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+# default: amars_lw as a radiation band, one C-ABI call per step
+# ---------------------------------------------------------------------------------------------
+def bench_band(ctx, args, nwave, ncol, nlyr, steps, warmup, hbm_peak, hbm_src):
+    import torch
+    from pyharp_b200 import fp64_peak_tflops, workloads as W
+    dev, world, rank = ctx.dev, ctx.world, ctx.rank
+    bw = W.make_band("amars_lw", nwave=nwave, ncol=ncol, nlyr=nlyr, variant=rank)
+    band = W.band_of(bw)
+    t = lambda a: torch.from_numpy(a).to(dev)
+    d = dict(conc=t(bw.conc), dz=t(bw.dz), bc={k: t(v) for k, v in bw.bc.items()}, op={"pres": t(bw.pres), "temp": t(bw.temp)})
+    step = lambda: band.forward_band(d["conc"], d["dz"], d["bc"], d["op"], check=False)
+    for _ in range(warmup):
+        bflx = band.forward_band(d["conc"], d["dz"], d["bc"], d["op"])  # (check=True: raises on a failed solve)
+    assert bool(torch.isfinite(bflx).all())
+    band.stats()
+    ctx.clocks.start()
+    ms, ms_max = timed_region(ctx, step, steps)
+    clk = ctx.clocks.stop()
+    st = band.stats()
+    kernel_ms = st["solve_kernel_ms"] / max(1, st["solves_timed"])
+    launches_per_step = st["kernel_launches"]
+    value = bw.nsolve * world * steps / (ms_max * 1e-3)
+
+    # ---- optics stage alone (HBM-bound streaming kernel): algorithmic bytes = inputs once + prop once
+    import ctypes as C
+    prop = band.optics(d["conc"], d["dz"], d["op"])
+    io, keep = band._io(d["conc"], d["dz"], None, d["op"], dev)  # raw C-ABI calls: no per-call tensor plumbing
+    io.prop = prop.data_ptr()
+    oms, _ = timed_region(ctx, lambda: band._lib.b200_band_optical_props(band._h, C.byref(io)), 10)
+    oms /= 10
+    del keep
+    obytes = bw.conc.nbytes + bw.pres.nbytes + bw.temp.nbytes + prop.numel() * 8
+    optics = {"kernel": "band_optics_fused_kernel (2 RFM attenuators -> mixed prop)", "avg_ms": oms, "algorithmic_bytes": obytes,
+              "gbs": obytes / (oms * 1e-3) / 1e9, "frac_of_hbm_peak": obytes / (oms * 1e-3) / 1e9 / hbm_peak,
+              "values_per_s": prop.numel() / (oms * 1e-3),
+              "note": "compute/L1-bound, not HBM-bound: per value 2 x (4 table gathers, trilinear blend, exp); "
+                      "profiles/r02 has the ncu capture"}
+    del prop
+
+    # ---- end to end: host tensors through the same call
+    e2e = None
+    e2e_raw = None
+    if not args.no_e2e:
+        pin = lambda a: torch.from_numpy(a).pin_memory()
+        h = dict(conc=pin(bw.conc), dz=pin(bw.dz), bc={k: pin(v) for k, v in bw.bc.items()}, op={"pres": pin(bw.pres), "temp": pin(bw.temp)})
+        for _ in range(3):
+            out_h = band.forward_band(h["conc"], h["dz"], h["bc"], h["op"])
+        assert float((out_h - bflx.cpu()).abs().max() / bflx.abs().max()) < 1e-12
+        esteps = max(3, min(steps, 20))
+        dt = wall_region(ctx, lambda: band.forward_band(h["conc"], h["dz"], h["bc"], h["op"]), esteps)
+        e2e = {"value": bw.nsolve * world * esteps / dt, "unit": "solves/s", "h2d_bytes_per_step": int(bw.h2d_bytes()),
+               "d2h_bytes_per_step": int(out_h.nbytes), "steps": esteps, "ms_per_step": 1e3 * dt / esteps,
+               "api": "pyharp_b200.RadiationBand.forward_band(host tensors) -> b200_band_forward_host: conc / pres / temp / "
+                      "per-column boundary fields in, band flux (ncol, nlyr+1, 2) out"}
+        del h, out_h
+    del d
+    torch.cuda.empty_cache()
+
+    out = None
+    if rank == 0:
+        fp64_peak = fp64_peak_tflops(ctx.local)
+        wlp = W.make("amars_lw", nwave=nwave, ncol=1, nlyr=nlyr)  # for the W / Q figures of the shape
+        W_, Q_ = wlp.flops_per_solve(), wlp.bytes_per_solve()
+        out = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+               "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f64", "data": "synthetic",
+               "config": {"workload": f"amars_lw-shape synthetic band: {nwave} correlated-k g-points x {ncol} columns per GPU x "
+                                      f"{nlyr} layers, nstr={bw.nstr}, 2 RFM attenuators (CO2, H2O) on a synthetic ck table, "
+                                      f"flags={bw.flag_tokens}",
+                          "step": "conc/pres/temp resident in HBM -> fused optics -> layer2level + Planck pre-pass -> flux solve "
+                                  "with fused band integration -> (ncol, nlyr+1, 2): one b200_band_forward call",
+                          "solves_per_step_per_gpu": bw.nsolve, "nstr": bw.nstr, "nlyr": nlyr, "nwave": nwave,
+                          "ncol_per_gpu": ncol, "sharding": f"columns x{world}, no data-path collective",
+                          "l2": "optical properties (%.0f MB per step) and back-sweep workspace exceed the 126 MB L2; no "
+                                "explicit flush" % (bw.nsolve * nlyr * 8 / 1e6),
+                          "flops_per_solve_W": W_, "bytes_per_solve_Q": Q_},
+               "clocks": clk, "gpu_launches": launches_per_step * steps,
+               "kernel": {"name": "disort_flux_kernel<NOMOM, BAND>", "avg_ms": kernel_ms, "share_of_step": kernel_ms / (ms / steps),
+                          "solves_per_s": bw.nsolve / (kernel_ms * 1e-3), "workspace_bytes": st["workspace_bytes"]},
+               "roofline": roofline_of("amars_lw", W_, Q_, bw.nsolve, kernel_ms, fp64_peak, hbm_peak, hbm_src),
+               "e2e": e2e, "opacity": optics}
+    # ---- the round-1 end-to-end route (per-spectral-point fluxes back to the host), for comparison
+    if not args.no_e2e and not args.no_others:
+        r = solver_step_bench(ctx, "amars_lw", nwave, ncol, nlyr, max(3, steps // 4), 3, variant=rank, e2e_steps=3)
+        if rank == 0:
+            out["e2e_disort_forward"] = r["e2e"]
+            out["solver_level_step"] = {"value": r["nsolve"] * world * max(3, steps // 4) / (r["ms_max"] * 1e-3), "unit": "solves/s",
+                                        "kernel_ms": r["kernel_ms"],
+                                        "what": "prop resident in HBM -> Planck pre-pass -> solve + fused band integration (round-1 step)"}
+        del r
+        torch.cuda.empty_cache()
+    # ---- the other BASELINE.json configurations on this box (N = 1 only)
+    if not args.no_others and world == 1:
+        others = []
+        fp64_peak = fp64_peak_tflops(ctx.local)
+        for name, osteps in (("amars_sw", 10), ("lbl", 10), ("gcm", 4)):
+            nw, nc, nl = DEFAULT_NWAVE[name], DEFAULT_COLS[name], DEFAULT_NLYR[name]
+            tile = nc // GCM_SEED_COLS if name == "gcm" else 1
+            r = solver_step_bench(ctx, name, nw, nc, nl, osteps, 3, tile=tile)
+            wl = r["wl"]
+            roof = roofline_of(name, wl.flops_per_solve(), wl.bytes_per_solve(), r["nsolve"], r["kernel_ms"], fp64_peak, hbm_peak, hbm_src)
+            others.append({"workload": f"{name}: {nw} spectral points x {nc} columns x {nl} layers, nstr={wl.nstr}, nprop={r['nprop']}"
+                                       + (f" (a seeded block of {nc // tile} columns tiled {tile}x: {r['prop_bytes'] / 1e9:.1f} GB of inputs)" if tile > 1 else ""),
+                           "value": r["nsolve"] * osteps / (r["ms_max"] * 1e-3), "unit": "solves/s", "steps": osteps,
+                           "ms_per_step": r["ms_max"] / osteps, "kernel_ms": r["kernel_ms"],
+                           "executed_frac_of_fp64_peak": roof["frac"], "algorithmic_equiv_frac": roof["algorithmic_equiv"]["frac"],
+                           "dram_frac_of_hbm_peak": roof["hbm"].get("dram_frac_of_hbm_peak"), "stale": roof.get("stale"),
+                           "clocks": r["clocks"]})
+            del r, wl
+            torch.cuda.empty_cache()
+        out["other_workloads"] = others
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 4: 10^5 wavenumbers x 1 column, spectral points sharded over the ranks (strong scaling)
+# ---------------------------------------------------------------------------------------------
+def bench_wave_sharded(ctx, args, nwave, nlyr, steps, warmup):
+    import torch
+    from pyharp_b200 import Disort, shard as S, workloads as W
+    dev, world, rank = ctx.dev, ctx.world, ctx.rank
+    wl = W.make("lbl", nwave=nwave, ncol=1, nlyr=nlyr)
+    sh = S.Shard("wave", *S._split(nwave, world, rank), world, rank)  # spectral points, also at world = 1
+    w_all = np.full(nwave, 0.1)  # d(nu) of the 0.1 cm^-1 grid
+    prop, bc, _, w, _, _ = S.take(sh, wl.prop, wl.bc, None, w_all)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_prop, d_bc, d_w = t(prop), {k: t(v) for k, v in bc.items()}, t(w)
+    ds = Disort(wl.options().nwave(sh.size))
+
+    def step():
+        b = ds.forward_band(d_prop, d_bc, None, d_w, check=False)
+        if ctx.comm is not None:
+            ds.allreduce_band(b, ctx.comm)
+        return b
+
+    for _ in range(warmup):
+        bflx = step()
+    torch.cuda.synchronize()
+    assert int(ds.status().abs().sum()) == 0 and bool(torch.isfinite(bflx).all())
+    ds.stats()
+    ctx.clocks.start()
+    ms, ms_max = timed_region(ctx, step, steps)
+    clk = ctx.clocks.stop()
+    st = ds.stats()
+    kernel_ms = st["solve_kernel_ms"] / max(1, st["solves_timed"])
+    ar_ms = None
+    if ctx.comm is not None:
+        buf = bflx.clone()
+        _, ar = timed_region(ctx, lambda: ds.allreduce_band(buf, ctx.comm), 50)
+        ar_ms = ar / 50
+    # per-call latency with a synchronise after every call (what a host loop that consumes the result sees)
+    def sync_step():
+        step()
+        torch.cuda.synchronize()
+    lat = wall_region(ctx, sync_step, steps) / steps
+    if rank != 0:
+        return None
+    return {"metric": "DISORT solves/sec (line-by-line, nstr=4, 40 layers, spectral points sharded)", "value": nwave * steps / (ms_max * 1e-3),
+            "unit": "solves/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_max / steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"lbl-shape synthetic: {nwave} wavenumbers x 1 column x {nlyr} layers, nstr={wl.nstr}, nprop=2, "
+                                   f"spectral points sharded over {world} GPU(s): {sh.size} per GPU",
+                       "step": "prop slice resident in HBM -> flux solve with fused band integration (warp-reduced L2 "
+                               "reductions) -> one ncclAllReduce(sum, f64) of the (1, nlyr+1, 2) band flux",
+                       "sharding": f"spectral points x{world}", "solves_per_step_per_gpu": sh.size, "nstr": wl.nstr, "nlyr": nlyr},
+            "clocks": clk, "gpu_launches": 2 * steps,
+            "kernel": {"name": "disort_flux_kernel<NOMOM, BAND=warp-reduced>", "avg_ms": kernel_ms, "share_of_step": kernel_ms / (ms / steps)},
+            "latency_ms_per_call_synchronised": 1e3 * lat, "allreduce_ms": ar_ms,
+            "resident_waves": sh.size / (148 * 4 * 128.0),
+            "e2e": None}
 
 
 if __name__ == "__main__":

@@ -324,6 +324,20 @@ class Disort:
             raise RuntimeError(f"b200disort_solve_band failed: {_cabi.strerror(rc)}")
         return bflx
 
+    def allreduce_band(self, bflx, comm):
+        """In-place sum of a device band flux (ncol, nlev, 2) over the ranks of an NCCL communicator
+        (b200disort_allreduce_band; `comm`: ncclComm_t as an int, e.g. pyharp_b200.nccl.Communicator) -- the one
+        collective of spectral-point sharding (examples/amars_lw.cpp:88 across ranks)."""
+        if not (bflx.is_cuda and bflx.is_contiguous() and bflx.dtype == torch.float64):
+            raise ValueError("allreduce_band: contiguous float64 CUDA tensor required")
+        if bflx.numel() != self.options.ncol() * self.nlev * 2:
+            raise ValueError("allreduce_band: bflx must be (ncol, nlev, 2)")
+        with torch.cuda.device(self.device):
+            rc = self._lib.b200disort_allreduce_band(self._h, bflx.data_ptr(), C.c_void_p(int(comm)))
+        if rc != _cabi.OK:
+            raise RuntimeError(f"b200disort_allreduce_band failed: {_cabi.strerror(rc)}")
+        return bflx
+
     def get_rad(self, options=None):
         """Intensities of the last forward(), shape (nwave, ncol, nphi, ntau, numu): cdisort's `uu` memory order
         (numu fastest) behind the (wave, column) batch axes.  pyharp only prints this tensor
