@@ -74,6 +74,9 @@ class DisortImpl : public torch::nn::Cloneable<DisortImpl> {
 
   DisortImpl() = default;
   explicit DisortImpl(DisortOptions const& options_);
+  //! A copy owns its own solver handle (torch::nn::Cloneable::clone() copy-constructs and then calls reset()).
+  DisortImpl(DisortImpl const& other);
+  DisortImpl& operator=(DisortImpl const& other);
   ~DisortImpl() override;
   void reset() override;
 
@@ -102,7 +105,9 @@ class DisortImpl : public torch::nn::Cloneable<DisortImpl> {
 
  private:
   void release();
+  void create_handle(int device);
   b200disort_handle* handle_ = nullptr;
+  int device_ = -1;  // CUDA device the handle lives on
   unsigned flags_ = 0;
   std::vector<double> utau_, umu_, phi_;
   torch::Tensor status_;

@@ -7,6 +7,10 @@
 
 #include <b200disort.h>
 
+#include <c10/cuda/CUDAFunctions.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -68,6 +72,26 @@ unsigned DisortOptions::flag_bits() {
 
 DisortImpl::DisortImpl(DisortOptions const& options_) : options(options_) { reset(); }
 
+// The handle (device workspace, tables) is never shared between copies: a copy starts without one and builds its own
+// in reset(); ds().utau / umu / phi are re-pointed at the copy's own vectors there.
+DisortImpl::DisortImpl(DisortImpl const& other)
+    : torch::nn::Cloneable<DisortImpl>(other), options(other.options), handle_(nullptr), device_(other.device_) {
+  if (other.handle_) reset();
+}
+
+DisortImpl& DisortImpl::operator=(DisortImpl const& other) {
+  if (this != &other) {
+    release();
+    torch::nn::Cloneable<DisortImpl>::operator=(other);
+    options = other.options;
+    device_ = other.device_;
+    status_ = torch::Tensor();
+    have_rad_ = false;
+    if (other.handle_) reset();
+  }
+  return *this;
+}
+
 DisortImpl::~DisortImpl() { release(); }
 
 void DisortImpl::release() {
@@ -95,6 +119,13 @@ void DisortImpl::reset() {
     TORCH_CHECK((int)options.wave_lower().size() == options.nwave() && (int)options.wave_upper().size() == options.nwave(),
                 "disort: planck needs wave_lower/wave_upper of length nwave");
 
+  // the handle lives on the caller's current CUDA device until a forward() brings a tensor from another one
+  create_handle(device_ >= 0 ? device_ : (int)c10::cuda::current_device());
+}
+
+void DisortImpl::create_handle(int device) {
+  release();
+  disort_state const& d = options.ds();
   b200disort_config cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.nwave = options.nwave(); cfg.ncol = options.ncol(); cfg.nlyr = d.nlyr;
@@ -104,10 +135,12 @@ void DisortImpl::reset() {
   cfg.user_tau = d.utau; cfg.user_mu = d.umu; cfg.user_phi = d.phi;
   cfg.wave_lower = options.wave_lower().empty() ? nullptr : options.wave_lower().data();
   cfg.wave_upper = options.wave_upper().empty() ? nullptr : options.wave_upper().data();
-  cfg.device = 0;
-  cfg.stream = nullptr;  // torch's default (legacy) stream
+  cfg.device = device;
+  c10::cuda::CUDAGuard guard((c10::DeviceIndex)device);
+  cfg.stream = c10::cuda::getCurrentCUDAStream((c10::DeviceIndex)device).stream();
   int rc = b200disort_create(&cfg, &handle_);
   TORCH_CHECK(rc == B200DISORT_OK, "disort: b200disort_create failed: ", b200disort_strerror(rc));
+  device_ = device;
   have_rad_ = false;
 }
 
@@ -122,6 +155,16 @@ torch::Tensor DisortImpl::forward(torch::Tensor prop, std::map<std::string, torc
   const bool on_host = !prop.is_cuda();
   const auto dev = prop.device();
   prop = prop.contiguous();
+  // the solve runs on prop's device (one rank per GPU: a caller on cuda:1 must not be sent to cuda:0) and on the
+  // caller's current stream of that device, so it is ordered after the producers of prop and before its consumers;
+  // the caller's current device is left as it was
+  const int want = on_host ? device_ : (int)dev.index();
+  if (want != device_) create_handle(want);
+  c10::cuda::CUDAGuard guard((c10::DeviceIndex)device_);
+  {
+    int rc = b200disort_set_stream(handle_, c10::cuda::getCurrentCUDAStream((c10::DeviceIndex)device_).stream());
+    TORCH_CHECK(rc == B200DISORT_OK, "disort: b200disort_set_stream failed: ", b200disort_strerror(rc));
+  }
 
   b200disort_bc b;
   std::memset(&b, 0, sizeof(b));
@@ -199,6 +242,7 @@ torch::Tensor DisortImpl::get_rad(torch::TensorOptions op) const {
   const int numu = (flags_ & B200DISORT_USRANG) ? d.numu : d.nstr;
   auto out = torch::empty({options.nwave(), options.ncol(), d.nphi, nlev, numu},
                           torch::TensorOptions().dtype(torch::kDouble).device(op.device()));
+  c10::cuda::CUDAGuard guard((c10::DeviceIndex)device_);
   int rc = b200disort_get_rad(handle_, out.data_ptr<double>());
   TORCH_CHECK(rc == B200DISORT_OK, "disort: get_rad failed: ", b200disort_strerror(rc));
   return out.to(op.dtype());

@@ -12,6 +12,9 @@
 
 #include <b200opacity.h>
 
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
+
 namespace harp {
 
 template <int N>
@@ -30,9 +33,11 @@ void call_interpn_cuda(at::TensorIterator& iter, at::Tensor kdata, at::Tensor ax
   if (c.numel() == out.numel() && ndim == 1 && nval > 1) c = c.view({npoint, nval}).select(1, 0).contiguous();
   TORCH_CHECK(c.numel() == npoint * ndim, "call_interpn_cuda: coordinate / output shape mismatch");
   at::Tensor o = out.is_contiguous() ? out : at::empty_like(out, at::MemoryFormat::Contiguous);
+  // on the output's device and the caller's current stream of that device
+  c10::cuda::CUDAGuard guard(out.device());
   int rc = b200_interpn(c.data_ptr<double>(), (long)npoint, ndim, kdata.contiguous().data_ptr<double>(),
                         axis.contiguous().data_ptr<double>(), hdims.data_ptr<int64_t>(), ndim, nval,
-                        o.data_ptr<double>(), nullptr);
+                        o.data_ptr<double>(), c10::cuda::getCurrentCUDAStream(out.device().index()).stream());
   TORCH_CHECK(rc == 0, "b200_interpn failed with code ", rc);
   if (!out.is_contiguous()) out.copy_(o);
 }

@@ -8,6 +8,10 @@
 #include <disort/disort_formatter.hpp>
 #include <disort/scattering_moments.hpp>
 
+#include <c10/cuda/CUDAFunctions.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
+
 static disort::DisortOptions test1a_options() {
   disort::DisortOptions op;
   op.header("running disort example");
@@ -85,6 +89,82 @@ TEST(Shim, longwave_host_equals_device_and_any_module) {
   EXPECT_TRUE(a.isfinite().all().item<bool>());
   EXPECT_GT(a.index({0, 0, 0, 0}).item<double>(), 0.);
   EXPECT_THROW(disort->get_rad(), c10::Error);
+}
+
+// Cloneable::clone() copy-constructs and calls reset() on the copy -- the copy must own its own solver
+// handle (the original stays usable, nothing is destroyed twice), also through copy assignment
+TEST(Shim, clone_and_copy_own_their_handles) {
+  const int nwave = 4, ncol = 2, nlyr = 12;
+  disort::DisortOptions op;
+  op.flags("lamber,quiet,onlyfl");
+  op.nwave(nwave).ncol(ncol);
+  op.ds().nlyr = nlyr;
+  op.ds().nstr = 8;
+  op.ds().nmom = 8;
+  disort::Disort disort(op);
+  torch::manual_seed(5);
+  auto prop = torch::rand({nwave, ncol, nlyr, 2}, torch::kDouble) * 0.9;
+  std::map<std::string, torch::Tensor> bc;
+  bc["fbeam"] = torch::ones({nwave, ncol}, torch::kDouble);
+  bc["umu0"] = torch::full({nwave, ncol}, 0.7, torch::kDouble);
+  auto a = disort->forward(prop, &bc);
+  {
+    auto c = std::dynamic_pointer_cast<disort::DisortImpl>(disort->clone());
+    ASSERT_TRUE(c != nullptr);
+    EXPECT_TRUE(torch::equal(c->forward(prop, &bc), a));
+    disort::DisortImpl copy(*disort);  // plain copy construction
+    EXPECT_TRUE(torch::equal(copy.forward(prop, &bc), a));
+    disort::DisortOptions other = op;
+    other.nwave(1);
+    disort::DisortImpl assigned(other);
+    assigned = *disort;  // copy assignment replaces the handle
+    EXPECT_TRUE(torch::equal(assigned.forward(prop, &bc), a));
+  }  // the copies and their handles are gone
+  EXPECT_TRUE(torch::equal(disort->forward(prop, &bc), a));
+  // a module holding the solver (harp::RadiationBand does) clones through register_module / AnyModule too
+  torch::nn::AnyModule any(disort);
+  auto any2 = any.clone();
+  EXPECT_TRUE(torch::equal(any2.forward(prop, &bc, torch::optional<torch::Tensor>()), a));
+}
+
+// launches go to the caller's CURRENT stream of the tensor's device (not the legacy stream), and the
+// caller's current device is left alone; with two GPUs the handle follows the tensor's device
+TEST(Shim, current_stream_and_device_are_respected) {
+  const int nwave = 6, ncol = 3, nlyr = 20;
+  disort::DisortOptions op;
+  op.flags("lamber,quiet,onlyfl");
+  op.nwave(nwave).ncol(ncol);
+  op.ds().nlyr = nlyr;
+  op.ds().nstr = 4;
+  op.ds().nmom = 4;
+  disort::Disort disort(op);
+  torch::manual_seed(7);
+  auto prop = torch::rand({nwave, ncol, nlyr, 2}, torch::kDouble) * 0.9;
+  std::map<std::string, torch::Tensor> bc;
+  bc["fbeam"] = torch::ones({nwave, ncol}, torch::kDouble);
+  bc["umu0"] = torch::full({nwave, ncol}, 0.4, torch::kDouble);
+  auto want = disort->forward(prop, &bc);
+  auto dev0 = torch::Device(torch::kCUDA, 0);
+  std::map<std::string, torch::Tensor> bcd;
+  for (auto& kv : bc) bcd[kv.first] = kv.second.to(dev0);
+  {
+    auto stream = c10::cuda::getStreamFromPool(false, 0);
+    c10::cuda::CUDAStreamGuard sg(stream);
+    // the producer of prop runs on this stream right before the solve: no explicit synchronisation in between
+    auto pd = (prop.to(dev0) * 2.0) * 0.5;
+    auto got = disort->forward(pd, &bcd);
+    EXPECT_TRUE(torch::equal(got.cpu(), want));
+  }
+  if (torch::cuda::device_count() > 1) {
+    auto dev1 = torch::Device(torch::kCUDA, 1);
+    std::map<std::string, torch::Tensor> bc1;
+    for (auto& kv : bc) bc1[kv.first] = kv.second.to(dev1);
+    auto got = disort->forward(prop.to(dev1), &bc1);
+    EXPECT_TRUE(got.device() == dev1);
+    EXPECT_TRUE(torch::equal(got.cpu(), want));
+    EXPECT_EQ((int)c10::cuda::current_device(), 0);
+    EXPECT_TRUE(torch::equal(disort->forward(prop.to(dev0), &bcd).cpu(), want));  // and back
+  }
 }
 
 TEST(Shim, bad_input_throws) {

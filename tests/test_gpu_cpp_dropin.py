@@ -23,7 +23,7 @@ def _run(exe, cwd=None):
 
 def test_cpp_shim(cuda_device):
     out = _run("test_shim")
-    assert "5 tests ran, 0 failed" in out
+    assert "7 tests ran, 0 failed" in out
 
 
 def test_reference_test_disort_unchanged(cuda_device):
