@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 import torch
 
+import golden_lib as G
 import oracle_lib as O
 from pyharp_b200 import Disort, workloads as W
 
@@ -47,6 +48,7 @@ def test_flux_parity(cuda_device, name, kw, where):
     assert flx.shape == ref.shape
     err = _relerr(flx.cpu().numpy(), ref)
     assert err < RTOL, err
+    assert G.diverr(flx.cpu().numpy(), ref) < RTOL  # net-flux divergence per layer (what the heating rate consumes)
     assert int(ds.status().abs().sum()) == 0
     assert ds.stats()["kernel_launches"] >= 1
 
@@ -95,9 +97,9 @@ def test_golden_fixtures(cuda_device, name):
     ds = Disort(wl.options())
     t = lambda a: None if a is None else torch.from_numpy(a).to(cuda_device)
     flx = ds.forward(t(wl.prop), {k: t(v) for k, v in wl.bc.items()}, t(wl.temf)).cpu().numpy()
-    assert G.relerr(flx, ld) < RTOL
+    G.check(flx, ld, RTOL)  # fluxes and per-layer net-flux divergence
     if ind is not None:
-        assert G.relerr(flx, ind, valid) < RTOL
+        G.check(flx, ind, RTOL, valid)
 
 
 @pytest.mark.parametrize("nstr", [2, 4, 6, 8, 12, 16, 24, 32])
@@ -129,3 +131,4 @@ def test_every_stream_count(cuda_device, nstr, thermal):
     t = lambda a: None if a is None else torch.from_numpy(a).to(cuda_device)
     flx = ds.forward(t(prop), {k: t(v) for k, v in bc.items()}, t(temf)).cpu().numpy()
     assert _relerr(flx, ref) < RTOL
+    assert G.diverr(flx, ref) < RTOL
