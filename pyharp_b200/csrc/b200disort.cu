@@ -706,7 +706,7 @@ extern "C" int b200disort_solve_host(b200disort_handle* h, const double* prop, i
     p.s0 = s0;
     p.nlocal = n;
     if (ck < nslot) CU_TRY(cudaStreamWaitEvent(sl.stream, h->ev_pre, 0));
-    rc = launch_flux(h, p, sl.stream, &sl.d_ws, &sl.ws_bytes, false);
+    rc = launch_flux(h, p, sl.stream, &sl.d_ws, &sl.ws_bytes, true);  // timed: b200disort_get_stats sees the host route too
     if (rc != B200DISORT_OK) return rc;
     if (stage) {
       CU_TRY(cudaMemcpyAsync(sl.h_buf + (size_t)chunk * in_per, d_flx,

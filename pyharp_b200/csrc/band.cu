@@ -37,6 +37,10 @@ struct DevAtt {
   const double* klnp;   // RFM reference atmosphere [nref]
   const double* ktemp;
   int on_grid;          // RFM: every spectral point coincides with its own table row (wi = (w, .), ww = (1, 0))
+  int sm_off;           // RFM: offset (doubles) of this attenuator's axes in the CTA's shared memory:
+                        //      [ln p ref (nlyr) | T ref (nlyr) | ln p axis (n1) | dT axis (n2)]
+  int same_axes;        // RFM: axes and reference atmosphere identical to the previous RFM attenuator's (same table
+                        //      file): its reference temperature, bracketing rows and blend weights are reused
   const int* wi;        // RFM (nwave, 2): table rows a spectral point blends (it sits on the table's own grid)
   const double* ww;     // RFM (nwave, 2): weight of row wi[.][0] (harp::interpn's b / den) and of wi[.][1] (a / den)
   const double* kw;     // AEROSOL (nwave, 2): (k_ext, ssa) at every spectral point
@@ -45,6 +49,7 @@ struct DevAtt {
 struct BandOpticsParams {
   DevAtt att[B200_BAND_MAX_ATT];
   int natt, nwave, nlyr, nspecies, nprop, exact;
+  int sm_doubles;  // shared memory of the axes (all RFM attenuators)
   long npoint;  // ncol * nlyr
   const double *conc, *pres, *temp, *dz;
   double eps;
@@ -74,12 +79,27 @@ __device__ __forceinline__ void ld_nc_v4(const double* p, double (&v)[4]) {
   asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
 }
 
-template <int WT>
-__global__ void __launch_bounds__(256) band_optics_fused_kernel(const BandOpticsParams P) {
+template <int WT, int MINB = 2>
+__global__ void __launch_bounds__(256, MINB) band_optics_fused_kernel(const BandOpticsParams P) {
   const int w0 = blockIdx.x * WT;
   const int nw = min(WT, P.nwave - w0);
+  // the interpolation axes live in shared memory: the bisections of harp::locate are chains of dependent loads at
+  // addresses that differ from lane to lane -- from global memory each of them costs the L1 a wavefront per lane
+  extern __shared__ double b200_axes[];
+  for (int a = 0; a < P.natt; ++a) {
+    const DevAtt& A = P.att[a];
+    if (A.type != B200_ATT_RFM || A.same_axes) continue;
+    double* s = b200_axes + A.sm_off;
+    const int n = P.nlyr;
+    for (int k = threadIdx.x; k < 2 * n + A.n1 + A.n2; k += blockDim.x)
+      s[k] = k < n ? A.klnp[k] : k < 2 * n ? A.ktemp[k - n] : A.kaxis[A.n0 + (k - 2 * n)];
+  }
+  __syncthreads();
   for (long i = (long)blockIdx.y * blockDim.x + threadIdx.x; i < P.npoint; i += (long)gridDim.y * blockDim.x) {
     double ext[WT], sse[WT];
+    // state shared by consecutive RFM attenuators on the same axes
+    double lnp = 0.0, dT = 0.0, wp1 = 0.0, wp2 = 0.0, wt1 = 0.0, wt2 = 0.0;
+    int ip1 = 0, ip2 = 0, it1 = 0, it2 = 0;
 #pragma unroll
     for (int k = 0; k < WT; ++k) { ext[k] = 0.0; sse[k] = 0.0; }
     for (int a = 0; a < P.natt; ++a) {
@@ -98,12 +118,19 @@ __global__ void __launch_bounds__(256) band_optics_fused_kernel(const BandOptics
       }
       // RFMImpl::forward (src/opacity/rfm.cpp:122-169); get_reftemp interpolates on a reference grid of length
       // nlyr (rfm.cpp:178: dims = {nlyr}), reproduced as is
-      const double lnp = log(P.pres[i]);
-      Dims r{};
-      r.len[0] = P.nlyr; r.stride[0] = 1; r.axis_off[0] = 0;
-      double tref;
-      interpn_dev<1, 1>(&tref, &lnp, A.ktemp, A.klnp, r, 0);
-      const double dT = __dsub_rn(P.temp[i], tref);
+      const double* sax = b200_axes + A.sm_off;
+      if (!A.same_axes) {
+        lnp = log(P.pres[i]);
+        Dims r{};
+        r.len[0] = P.nlyr; r.stride[0] = 1; r.axis_off[0] = 0;
+        double tref;
+        interpn_dev<1, 1>(&tref, &lnp, sax + P.nlyr, sax, r, 0);
+        dT = __dsub_rn(P.temp[i], tref);
+        if (!P.exact) {
+          bracket_dev(sax + 2 * P.nlyr, A.n1, lnp, ip1, ip2, wp1, wp2);
+          bracket_dev(sax + 2 * P.nlyr + A.n1, A.n2, dT, it1, it2, wt1, wt2);
+        }
+      }
       if (P.exact) {
         Dims d{};
         d.len[0] = A.n0; d.len[1] = A.n1; d.len[2] = A.n2;
@@ -117,10 +144,6 @@ __global__ void __launch_bounds__(256) band_optics_fused_kernel(const BandOptics
             ext[k] = __dadd_rn(ext[k], __dmul_rn(__dmul_rn(1.0e-3, exp(v)), cv));
           }
       } else {
-        int ip1, ip2, it1, it2;
-        double wp1, wp2, wt1, wt2;
-        bracket_dev(A.kaxis + A.n0, A.n1, lnp, ip1, ip2, wp1, wp2);
-        bracket_dev(A.kaxis + A.n0 + A.n1, A.n2, dT, it1, it2, wt1, wt2);
         // transposed table (n1, n2, n0): the WT values a corner contributes are contiguous (whole 32-byte sectors
         // per load instead of one double of each), and neighbouring layers -- the lanes of a warp -- read
         // neighbouring rows
@@ -201,12 +224,17 @@ __global__ void aerosol_wave_kernel(const double* __restrict__ kwave, const doub
 
 // acc_t (rows, ncol) -> bflx (ncol, rows): the band-flux buffer the solve kernel accumulates into is column-fastest
 // (coalesced reductions), pyharp's tensor is (ncol, nlyr+1, 2)
-__global__ void band_finish_kernel(const double* __restrict__ acc, int rows, int ncol, double* __restrict__ bflx) {
+// (nrep replicas of acc, added in replica order: the warp-reduced form of the solve kernel spreads its reductions)
+__global__ void band_finish_kernel(const double* __restrict__ acc, int rows, int ncol, int nrep, double* __restrict__ bflx) {
   __shared__ double tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int dr = threadIdx.y; dr < 32; dr += blockDim.y) {
     const int r = r0 + dr, c = c0 + threadIdx.x;
-    if (r < rows && c < ncol) tile[dr][threadIdx.x] = acc[(long)r * ncol + c];
+    if (r < rows && c < ncol) {
+      double v = 0.0;
+      for (int k = 0; k < nrep; ++k) v += acc[((long)k * rows + r) * ncol + c];
+      tile[dr][threadIdx.x] = v;
+    }
   }
   __syncthreads();
   for (int dc = threadIdx.y; dc < 32; dc += blockDim.y) {
@@ -325,20 +353,46 @@ int launch_optics(b200_band* b, cudaStream_t st, int cc, const double* conc, con
   P.eps = b->eps;
   P.prop = prop;
   const unsigned gy = blocks_for(P.npoint, 256, 65535);
+  // shared memory of the interpolation axes: offsets per RFM attenuator (those on the previous one's axes share)
+  int smd = 0;
+  for (int a = 0; a < b->natt; ++a) {
+    if (P.att[a].type != B200_ATT_RFM) continue;
+    if (P.att[a].same_axes) { P.att[a].sm_off = P.att[a - 1].sm_off; continue; }
+    P.att[a].sm_off = smd;
+    smd += 2 * nlyr + P.att[a].n1 + P.att[a].n2;
+  }
+  P.sm_doubles = smd;
+  const size_t sm = (size_t)smd * sizeof(double);
   // enough points to fill the machine with tiles of 8 spectral points per thread?  otherwise one per thread
-  static const int env_wt = std::getenv("B200_BAND_WT") ? std::atoi(std::getenv("B200_BAND_WT")) : 0;  // profiling knob
-  const int wt = env_wt ? env_wt : (nwave >= 16 ? 16 : 8);
-  if (wt == 16 && P.npoint * ((nwave + 15) / 16) >= (long)h->sm_count * 2048)
-    band_optics_fused_kernel<16><<<dim3((unsigned)((nwave + 15) / 16), gy), 256, 0, st>>>(P);
-  else if (wt == 32 && P.npoint * ((nwave + 31) / 32) >= (long)h->sm_count * 2048)
-    band_optics_fused_kernel<32><<<dim3((unsigned)((nwave + 31) / 32), gy), 256, 0, st>>>(P);
-  else if (P.npoint * ((nwave + 7) / 8) >= (long)h->sm_count * 2048)
-    band_optics_fused_kernel<8><<<dim3((unsigned)((nwave + 7) / 8), gy), 256, 0, st>>>(P);
-  else
-    band_optics_fused_kernel<1><<<dim3((unsigned)nwave, gy), 256, 0, st>>>(P);
+  static const int env_wt = std::getenv("B200_BAND_WT") ? std::atoi(std::getenv("B200_BAND_WT")) : 0;  // profiling knob: 10 * WT + MINB
+  const int sel = env_wt ? env_wt : (nwave >= 16 ? 162 : 82);
+  const int wt = sel / 10;
+  const bool big = P.npoint * ((nwave + wt - 1) / wt) >= (long)h->sm_count * 2048;
+#define B200_OPT(WT_, MB_) band_optics_fused_kernel<WT_, MB_><<<dim3((unsigned)((nwave + WT_ - 1) / WT_), gy), 256, sm, st>>>(P)
+  if (!big) B200_OPT(1, 2);
+  else if (sel == 82) B200_OPT(8, 2);
+  else if (sel == 83) B200_OPT(8, 3);
+  else if (sel == 84) B200_OPT(8, 4);
+  else if (sel == 163) B200_OPT(16, 3);
+  else if (sel == 164) B200_OPT(16, 4);
+  else if (sel == 322) B200_OPT(32, 2);
+  else if (sel == 42) B200_OPT(4, 2);
+  else if (sel == 44) B200_OPT(4, 4);
+  else if (sel == 46) B200_OPT(4, 6);
+  else B200_OPT(16, 2);
+#undef B200_OPT
   CU_TRY(cudaGetLastError());
   h->stats.kernel_launches += 1;
   return B200DISORT_OK;
+}
+
+// warp-reduced band integration (emit_flux, BAND = 2): fewer than 32 columns, a power of two, nstr <= 8
+constexpr int kBandReplicas = 64;
+int band_warp_red(const b200disort_handle* h, int cc) {
+  return (h->inst && h->inst->nn <= 4 && cc < 32 && (cc & (cc - 1)) == 0) ? cc : 0;
+}
+size_t band_acc_doubles(const b200disort_handle* h, int rows, int cc) {
+  return (size_t)(band_warp_red(h, cc) ? kBandReplicas : 1) * rows * cc;
 }
 
 // every kernel of the band pipeline for one chunk of columns, on `st`
@@ -380,13 +434,15 @@ int run_chunk(b200_band* b, cudaStream_t st, const Chunk& c, const double* d_dz,
     if (rc != B200DISORT_OK) return rc;
     h->stats.kernel_launches += 1;
   } else {
-    CU_TRY(cudaMemsetAsync(c.acc, 0, (size_t)rows * cc * sizeof(double), st));
     p.bflx_t = c.acc;
     p.weights = b->d_weights;
-    p.warp_red = (cc < 32 && (cc & (cc - 1)) == 0) ? cc : 0;
+    p.warp_red = band_warp_red(h, cc);
+    p.nrep = p.warp_red ? kBandReplicas : 1;
+    p.rep_stride = (long)rows * cc;
+    CU_TRY(cudaMemsetAsync(c.acc, 0, (size_t)p.nrep * rows * cc * sizeof(double), st));
     int rc = launch_flux(h, p, st, ws, ws_bytes, true);
     if (rc != B200DISORT_OK) return rc;
-    band_finish_kernel<<<dim3((unsigned)((cc + 31) / 32), (unsigned)((rows + 31) / 32)), dim3(32, 8), 0, st>>>(c.acc, rows, cc, c.bflx);
+    band_finish_kernel<<<dim3((unsigned)((cc + 31) / 32), (unsigned)((rows + 31) / 32)), dim3(32, 8), 0, st>>>(c.acc, rows, cc, p.nrep, c.bflx);
     CU_TRY(cudaGetLastError());
     h->stats.kernel_launches += 1;
   }
@@ -470,6 +526,16 @@ extern "C" int b200_band_create(const b200_band_config* cfg, b200_band** out) {
         wi[2 * w] = i1; wi[2 * w + 1] = i2;
         if (x2 != x1) { ww[2 * w] = (x2 - cw) / (x2 - x1); ww[2 * w + 1] = (cw - x1) / (x2 - x1); }
         else { ww[2 * w] = 1.0; ww[2 * w + 1] = 0.0; }  // (v1 + v2) / 2 of the same row
+      }
+      // same axes and reference atmosphere as the previous attenuator (two species of one table file)?
+      D.same_axes = 0;
+      if (a > 0 && cfg->att[a - 1].type == B200_ATT_RFM) {
+        const b200_attenuator& Pv = cfg->att[a - 1];
+        bool same = Pv.dims[0] == A.dims[0] && Pv.dims[1] == A.dims[1] && Pv.dims[2] == A.dims[2] && Pv.nref == A.nref;
+        if (same) same = std::memcmp(Pv.kaxis, A.kaxis, sizeof(double) * (size_t)(D.n0 + D.n1 + D.n2)) == 0 &&
+                         std::memcmp(Pv.klnp, A.klnp, sizeof(double) * (size_t)dc.nlyr) == 0 &&
+                         std::memcmp(Pv.ktemp, A.ktemp, sizeof(double) * (size_t)dc.nlyr) == 0;
+        D.same_axes = same ? 1 : 0;
       }
       D.on_grid = 1;
       for (int w = 0; w < D.n0; ++w)
@@ -557,7 +623,7 @@ extern "C" int b200_band_forward(b200_band* b, const b200_band_io* io) {
   // scratch: [prop?] [temf] [pkag] [acc] [status?]
   const size_t n_prop = io->prop ? 0 : r4(ns * nlyr * b->nprop);
   const size_t n_temf = b->planck ? r4((size_t)ncol * (nlyr + 1)) : 0, n_pkag = b->planck ? r4((size_t)h->nband * ncol * (nlyr + 1)) : 0;
-  const size_t n_acc = io->flx ? 0 : r4((size_t)b->nlev * 2 * ncol), n_st = io->status ? 0 : r4((ns * sizeof(int32_t) + 7) / 8);
+  const size_t n_acc = io->flx ? 0 : r4(band_acc_doubles(h, b->nlev * 2, ncol)), n_st = io->status ? 0 : r4((ns * sizeof(int32_t) + 7) / 8);
   rc = ensure_dev(&b->d_main, &b->main_bytes, (n_prop + n_temf + n_pkag + n_acc + n_st + 1) * sizeof(double));
   if (rc != B200DISORT_OK) return rc;
   const double* d_dz = nullptr;
@@ -657,7 +723,10 @@ extern "C" int b200_band_forward_host(b200_band* b, const b200_band_io* io) {
   const size_t n_conc = r4((size_t)cc * nlyr * nsp), n_pt = r4((size_t)cc * nlyr);
   const size_t n_in = n_conc + (io->pres ? n_pt : 0) + (io->temp ? n_pt : 0) + (io->rho ? n_pt : 0) + n_bc * r4(bc_len);
   const size_t n_prop = r4(ns * nlyr * b->nprop), n_temf = b->planck ? r4((size_t)cc * (nlyr + 1)) : 0;
-  const size_t n_pkag = b->planck ? r4((size_t)h->nband * cc * (nlyr + 1)) : 0, n_acc = r4((size_t)nlev * 2 * cc);
+  size_t acc_max = 0;  // (the last chunk may be a narrower, warp-reduced one with replicas)
+  for (long k = 0; k + 1 < (long)cstart.size(); ++k)
+    acc_max = std::max(acc_max, band_acc_doubles(h, nlev * 2, (int)(cstart[k + 1] - cstart[k])));
+  const size_t n_pkag = b->planck ? r4((size_t)h->nband * cc * (nlyr + 1)) : 0, n_acc = r4(acc_max);
   const size_t n_bflx = r4((size_t)cc * nlev * 2), n_dT = io->dTdt ? n_pt : 0, n_st = r4((ns * sizeof(int32_t) + 7) / 8);
   const size_t slot_doubles = n_in + n_prop + n_temf + n_pkag + n_acc + n_bflx + n_dT + n_st;
 
@@ -808,7 +877,8 @@ extern "C" int b200disort_solve_band(b200disort_handle* h, const double* prop, i
   CU_TRY(cudaEventRecord(h->ev0, st));
   const int rows = (c.nlyr + 1) * 2;
   const size_t n_pkag = planck ? (size_t)h->nband * c.ncol * (c.nlyr + 1) : 0;
-  int rc = ensure_dev(&h->d_acc, &h->acc_bytes, ((size_t)rows * c.ncol + n_pkag) * sizeof(double));
+  const size_t n_acc = band_acc_doubles(h, rows, c.ncol);
+  int rc = ensure_dev(&h->d_acc, &h->acc_bytes, (n_acc + n_pkag) * sizeof(double));
   if (rc != B200DISORT_OK) return rc;
   SolveParams p{};
   p.nwave = c.nwave; p.ncol = c.ncol; p.nlyr = c.nlyr; p.nprop = nprop; p.nstr = c.nstr;
@@ -823,19 +893,21 @@ extern "C" int b200disort_solve_band(b200disort_handle* h, const double* prop, i
   p.s0 = 0;
   p.nlocal = (long)c.nwave * c.ncol;
   if (planck) {
-    double* pkag = h->d_acc + (size_t)rows * c.ncol;
+    double* pkag = h->d_acc + n_acc;
     rc = launch_planck_into(h, temf, c.ncol, pkag, st);
     if (rc != B200DISORT_OK) return rc;
     p.pkag = pkag;
   }
-  CU_TRY(cudaMemsetAsync(h->d_acc, 0, (size_t)rows * c.ncol * sizeof(double), st));
+  CU_TRY(cudaMemsetAsync(h->d_acc, 0, n_acc * sizeof(double), st));
   p.bflx_t = h->d_acc;
   p.weights = weights;
-  p.warp_red = (c.ncol < 32 && (c.ncol & (c.ncol - 1)) == 0) ? c.ncol : 0;
+  p.warp_red = band_warp_red(h, c.ncol);
+  p.nrep = p.warp_red ? kBandReplicas : 1;
+  p.rep_stride = (long)rows * c.ncol;
   rc = launch_flux(h, p, st, &h->d_ws, &h->ws_bytes, true);
   if (rc != B200DISORT_OK) return rc;
   band_finish_kernel<<<dim3((unsigned)((c.ncol + 31) / 32), (unsigned)((rows + 31) / 32)), dim3(32, 8), 0, st>>>(h->d_acc, rows,
-                                                                                                               c.ncol, bflx);
+                                                                                                               c.ncol, p.nrep, bflx);
   CU_TRY(cudaGetLastError());
   h->stats.kernel_launches += 1;
   return B200DISORT_OK;

@@ -190,6 +190,10 @@ struct SolveParams {
   const double* weights;  // (nwave) band weights (BAND only)
   int bc_bcast;    // != 0: the boundary fields are (ncol) arrays shared by every spectral point
   int warp_red;    // BAND = 2: columns per warp (= ncol, a power of two <= 16), see emit_flux
+  int nrep;        // BAND = 2: replicas of the band-flux buffer; CTA b accumulates into replica b % nrep, the host's
+  long rep_stride; //   finishing kernel adds them (doubles per replica).  With one column every warp of the launch
+                   //   reduces into the SAME 2 (nlyr + 1) addresses: unreplicated, the L2 serialises ~3000 reductions
+                   //   per address and the fused form was 2x slower than writing the fluxes (10^5 x 1 line-by-line)
   double* ws;      // back-sweep workspace: [half][warp][level][elem][lane] (kWsLanes lanes per group)
   long ws_half;    // doubles per half (carried back sweep: two halves; otherwise unused)
   long ws_threads; // threads the workspace was sized for (a multiple of kWsLanes)
