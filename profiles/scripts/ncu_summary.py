@@ -5,9 +5,11 @@ import subprocess
 import sys
 
 rep, nsolve = sys.argv[1], float(sys.argv[2])
+kfilter = sys.argv[3] if len(sys.argv) > 3 else "disort_flux_kernel"  # substring of the kernel name to report
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
-h, u, v = rows[0], rows[1], rows[2]
+h, u = rows[0], rows[1]
+v = next((r for r in rows[2:] if kfilter in r[h.index("Kernel Name")]), rows[2])
 m = {n: (v[i], u[i]) for i, n in enumerate(h)}
 f = lambda k: float(m[k][0].replace(",", ""))
 dur_ms = f("gpu__time_duration.sum") * (1e-6 if m["gpu__time_duration.sum"][1] == "ns" else 1e-3 if m["gpu__time_duration.sum"][1] == "us" else 1.0)
@@ -18,7 +20,7 @@ wr = f("dram__bytes_write.sum") * unit[m["dram__bytes_write.sum"][1]]
 dfma = f("smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed") * cyc
 dmul = f("smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed") * cyc
 dadd = f("smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed") * cyc
-print(f"kernel               {m['launch__function_name'][0] if 'launch__function_name' in m else 'disort_flux_kernel'}")
+print(f"kernel               {m['Kernel Name'][0]}")
 print(f"duration             {dur_ms:.3f} ms for {nsolve:.0f} solves")
 print(f"registers/thread     {m['launch__registers_per_thread'][0]}   block {m['launch__block_size'][0]}  grid {m['launch__grid_size'][0]}")
 print(f"warps active         {f('sm__warps_active.avg.pct_of_peak_sustained_active'):.1f} % of max")

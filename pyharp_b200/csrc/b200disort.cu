@@ -533,6 +533,7 @@ extern "C" int b200disort_solve_host(b200disort_handle* h, const double* prop, i
   if (planck && !temf) return B200DISORT_ERR_INVALID;
   CU_TRY(cudaSetDevice(c.device));
   h->stats.kernel_launches = 0;
+  CU_TRY(cudaEventRecord(h->ev0, h->stream));  // (b200disort_get_stats measures from here)
   using Slot = b200disort_handle::Slot;
   if (!onlyfl || (c.flags & B200DISORT_USRTAU) || !h->inst) {
     // cold path (test_disort-sized batches): stage everything, one launch, copy back

@@ -510,6 +510,38 @@ B200_HD constexpr int bl_src(int i, int n) {
   return (i == 0) ? 0 : (i == 2) ? 1 : (i % 2 == 0) ? i - 2 : (i == n - 1) ? n - 2 : i + 2;
 }
 
+// Eigenvector accumulator Y of the Jacobi iteration: a thread-private array (registers / local memory), or -- nn >= 6,
+// -DB200_SMEM_Y=1 -- the thread's slice of the CTA's shared memory ([element][thread], conflict-free).  At nstr = 16
+// Y is 64 doubles = 128 registers of a 255-register thread that also holds G, L and the stack operator; ptxas spills
+// it and the hot loop streams it through L1/L2 (ncu: long_scoreboard 3.2 stalls per issue).  In shared memory its
+// columns are addressed at run time, so the Brent-Luk rounds permute an index vector instead of moving Y.
+#ifndef B200_SMEM_Y
+#define B200_SMEM_Y 0
+#endif
+template <int NN, bool SMEM>
+struct YRef;
+template <int NN>
+struct YRef<NN, false> {
+  static constexpr bool kSmem = false;
+  double (&a)[NN][NN];
+  B200_HD explicit YRef(double (&arr)[NN][NN]) : a(arr) {}
+  B200_HD double& operator()(int i, int j) const { return a[i][j]; }
+};
+#if defined(__CUDACC__)
+template <int NN>
+struct YRef<NN, true> {
+  static constexpr bool kSmem = true;
+  double* base;
+  int stride;
+  __device__ __forceinline__ explicit YRef(double (&)[NN][NN]) {
+    extern __shared__ __align__(128) double b200_smem[];
+    base = b200_smem + threadIdx.x;
+    stride = (int)blockDim.x;
+  }
+  __device__ __forceinline__ double& operator()(int i, int j) const { return base[(i * NN + j) * stride]; }
+};
+#endif
+
 // fully unrolled instantiation (small nn: registers)
 #define B200_UNROLL _Pragma("unroll")
 #define B200_FN(name) name##_u

@@ -97,6 +97,9 @@ cudaError_t upload_tables(const QuadTables* qt) { return cudaMemcpyToSymbol(c_qt
 // dynamic shared memory per CTA: the parked stack state (Ra packed symmetric + da) of every thread
 size_t smem_bytes(int block) {
   if (TmaRing<kNsave>::kUsed) return (size_t)(block / 32) * TmaRing<kNsave>::kWarpDoubles * sizeof(double);
+#if B200_SMEM_Y
+  if (B200_NN >= 6) return (size_t)(B200_NN * B200_NN) * block * sizeof(double);
+#endif
 #if B200_SMEM_STACK
   return (size_t)(B200_NN * (B200_NN + 1) / 2 + B200_NN) * block * sizeof(double);
 #else
