@@ -48,8 +48,17 @@ class Communicator:
         dist.broadcast_object_list(box, src=0)
         C.memmove(C.byref(uid), box[0], 128)
         self._comm = C.c_void_p()
-        with torch.cuda.device(device_index):
-            rc = L.ncclCommInitRank(C.byref(self._comm), self.world, uid, self.rank)
+        # NCCL announces its version on stdout at the first communicator; callers (bench.py) own stdout: send it to stderr
+        import sys
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            with torch.cuda.device(device_index):
+                rc = L.ncclCommInitRank(C.byref(self._comm), self.world, uid, self.rank)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
         if rc != 0:
             raise RuntimeError(f"ncclCommInitRank failed ({rc})")
         v = C.c_int(0)
