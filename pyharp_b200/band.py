@@ -171,6 +171,15 @@ class RadiationBand:
             self._lib.b200_band_destroy(h)
             self._h = None
 
+    def _use_current_stream(self):
+        """Launch on torch's current stream of the band's device (call inside torch.cuda.device(self.device))."""
+        st = torch.cuda.current_stream()
+        if st.cuda_stream != self._stream.cuda_stream:
+            rc = self._lib.b200disort_set_stream(self._lib.b200_band_solver(self._h), C.c_void_p(st.cuda_stream))
+            if rc != _cabi.OK:
+                raise RuntimeError(f"b200disort_set_stream failed: {_cabi.strerror(rc)}")
+            self._stream = st
+
     # ---- forward -----------------------------------------------------------------------------------------------
     def _io(self, conc, dz, bc, op, dev, rho=None, cp=None):
         nw, nc, nl = self.nwave, self.ncol, self.nlyr
@@ -247,6 +256,7 @@ class RadiationBand:
             status = torch.empty((self.nwave, self.ncol), dtype=torch.int32, device=dev, **pin)
             io.status = status.data_ptr()
         with torch.cuda.device(self.device):
+            self._use_current_stream()
             if on_host:
                 rc = self._lib.b200_band_forward_host(self._h, C.byref(io))
             else:
@@ -270,6 +280,7 @@ class RadiationBand:
         status = torch.empty((self.nwave, self.ncol), dtype=torch.int32, device=self.device)
         io.bflx, io.flx, io.prop, io.status = bflx.data_ptr(), flx.data_ptr(), prop.data_ptr(), status.data_ptr()
         with torch.cuda.device(self.device):
+            self._use_current_stream()
             rc = self._lib.b200_band_forward(self._h, C.byref(io))
             if rc == _cabi.OK:
                 rc = self._lib.b200_band_check(self._h, None)
@@ -287,6 +298,7 @@ class RadiationBand:
         prop = torch.empty((self.nwave, self.ncol, self.nlyr, self.nprop), dtype=torch.float64, device=self.device)
         io.prop = prop.data_ptr()
         with torch.cuda.device(self.device):
+            self._use_current_stream()
             rc = self._lib.b200_band_optical_props(self._h, C.byref(io))
         self._raise(rc)
         return prop
@@ -300,6 +312,7 @@ class RadiationBand:
         if not bflx.is_cuda or not bflx.is_contiguous():
             raise ValueError("allreduce: contiguous CUDA tensor required")
         with torch.cuda.device(self.device):
+            self._use_current_stream()
             rc = self._lib.b200_band_allreduce(self._h, bflx.data_ptr(), bflx.numel(), C.c_void_p(int(comm)))
         if rc != _cabi.OK:
             raise RuntimeError(f"b200_band_allreduce failed: {_cabi.strerror(rc)}")

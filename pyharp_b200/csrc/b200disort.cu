@@ -523,9 +523,24 @@ bool b200::is_pinned(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
+static int solve_host_impl(b200disort_handle* h, const double* prop, int nprop, const b200disort_bc* bc, const double* temf,
+                           double* flx, double* uu, int32_t* status);
+
 extern "C" int b200disort_solve_host(b200disort_handle* h, const double* prop, int nprop,
                                      const b200disort_bc* bc, const double* temf, double* flx,
                                      double* uu, int32_t* status) {
+  const int rc = solve_host_impl(h, prop, nprop, bc, temf, flx, uu, status);
+  if (h && rc != B200DISORT_OK && rc != B200DISORT_ERR_SOLVE && rc != B200DISORT_ERR_INVALID) {
+    // an error return must not leave copies in flight that still read or write the caller's (and the pinned) buffers
+    for (auto& sl : h->slots)
+      if (sl.stream) cudaStreamSynchronize(sl.stream);
+    cudaStreamSynchronize(h->stream);
+  }
+  return rc;
+}
+
+static int solve_host_impl(b200disort_handle* h, const double* prop, int nprop, const b200disort_bc* bc, const double* temf,
+                           double* flx, double* uu, int32_t* status) {
   if (!h || !prop || !flx || nprop < 1) return B200DISORT_ERR_INVALID;
   const b200disort_config& c = h->cfg;
   const bool planck = c.flags & B200DISORT_PLANCK;

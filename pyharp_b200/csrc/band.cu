@@ -677,7 +677,20 @@ extern "C" int b200_band_check(b200_band* b, int* n_bad) {
 
 constexpr long kChunkWaves = 4;
 
+static int band_forward_host_impl(b200_band* b, const b200_band_io* io);
+
 extern "C" int b200_band_forward_host(b200_band* b, const b200_band_io* io) {
+  const int rc = band_forward_host_impl(b, io);
+  if (b && rc != B200DISORT_OK && rc != B200DISORT_ERR_SOLVE && rc != B200DISORT_ERR_INVALID && rc != B200DISORT_ERR_UNSUPPORTED) {
+    // an error return must not leave copies in flight that still read or write the caller's buffers
+    for (auto& sl : b->slots)
+      if (sl.stream) cudaStreamSynchronize(sl.stream);
+    cudaStreamSynchronize(b->h->stream);
+  }
+  return rc;
+}
+
+static int band_forward_host_impl(b200_band* b, const b200_band_io* io) {
   int rc = check_io(b, io, true);
   if (rc != B200DISORT_OK) return rc;
   b200disort_handle* h = b->h;

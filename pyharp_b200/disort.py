@@ -186,7 +186,9 @@ class Disort:
                 setattr(cfg, name, p)
         if (flags & _cabi.PLANCK) and len(options.wave_lower()) != options.nwave():
             raise ValueError("planck needs wave_lower/wave_upper of length nwave")
-        cfg.device = self.device.index or 0
+        if self.device.index is None:  # device='cuda': the caller's current device, not GPU 0
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        cfg.device = self.device.index
         with torch.cuda.device(self.device):
             self._stream = torch.cuda.current_stream()
             cfg.stream = self._stream.cuda_stream
@@ -212,6 +214,16 @@ class Disort:
         d = self.options.ds()
         return d.ntau if self._flags & _cabi.USRTAU else d.nlyr + 1
 
+    def _use_current_stream(self):
+        """Launch on torch's CURRENT stream of the handle's device (call inside torch.cuda.device(self.device)): the
+        outputs are allocated by the caching allocator for that stream and the inputs were produced on it."""
+        st = torch.cuda.current_stream()
+        if st.cuda_stream != self._stream.cuda_stream:
+            rc = self._lib.b200disort_set_stream(self._h, C.c_void_p(st.cuda_stream))
+            if rc != _cabi.OK:
+                raise RuntimeError(f"b200disort_set_stream failed: {_cabi.strerror(rc)}")
+            self._stream = st
+
     def _check_shapes(self, prop, bc, temf):
         d = self.options.ds()
         nw, nc = self.options.nwave(), self.options.ncol()
@@ -220,6 +232,8 @@ class Disort:
         if prop.dtype != torch.float64:
             raise TypeError("prop must be float64")
         for k, v in (bc or {}).items():
+            if k == "fluor":  # accepted and unused, as in cdisort without general_source (the C++ shim does the same)
+                continue
             if k not in _cabi.BC.FIELDS:
                 raise KeyError(f"unknown boundary condition '{k}'")
             if tuple(v.shape) != (nw, nc):
@@ -244,6 +258,8 @@ class Disort:
         bcs = _cabi.BC()
         keep = [prop]
         for k, v in bc.items():
+            if k == "fluor":
+                continue
             v = v.to(device=dev, dtype=torch.float64).contiguous()
             keep.append(v)
             setattr(bcs, k, v.data_ptr())
@@ -262,6 +278,7 @@ class Disort:
             numu = d.numu if self._flags & _cabi.USRANG else d.nstr
             uu = torch.empty((nw, nc, d.nphi, self.nlev, numu), dtype=torch.float64, device=dev)
         with torch.cuda.device(self.device):
+            self._use_current_stream()
             fn = self._lib.b200disort_solve_host if on_host else self._lib.b200disort_solve
             rc = fn(self._h, prop.data_ptr(), prop.shape[3], C.byref(bcs), tptr, flx.data_ptr(),
                     None if uu is None else uu.data_ptr(), status.data_ptr())
@@ -283,6 +300,7 @@ class Disort:
 
     def forward_device_async(self, prop, bcs, temf_ptr, flx, status):
         """Raw device-pointer solve without synchronisation (used by bench.py's kernel-only leg)."""
+        self._use_current_stream()
         rc = self._lib.b200disort_solve(self._h, prop.data_ptr(), prop.shape[3], C.byref(bcs), temf_ptr,
                                         flx.data_ptr(), None, status.data_ptr())
         if rc != _cabi.OK:
@@ -300,6 +318,8 @@ class Disort:
         bcs = _cabi.BC()
         keep = [prop]
         for k, v in (bc or {}).items():
+            if k == "fluor":
+                continue
             v = v.to(device=self.device, dtype=torch.float64).contiguous()
             keep.append(v)
             setattr(bcs, k, v.data_ptr())
@@ -312,6 +332,7 @@ class Disort:
         bflx = torch.empty((nc, self.options.ds().nlyr + 1, 2), dtype=torch.float64, device=self.device)
         status = torch.empty((nw, nc), dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
+            self._use_current_stream()
             rc = self._lib.b200disort_solve_band(self._h, prop.data_ptr(), prop.shape[3], C.byref(bcs), tptr, w.data_ptr(),
                                                  bflx.data_ptr(), status.data_ptr())
             if rc == _cabi.OK and check:
@@ -333,6 +354,7 @@ class Disort:
         if bflx.numel() != self.options.ncol() * self.nlev * 2:
             raise ValueError("allreduce_band: bflx must be (ncol, nlev, 2)")
         with torch.cuda.device(self.device):
+            self._use_current_stream()
             rc = self._lib.b200disort_allreduce_band(self._h, bflx.data_ptr(), C.c_void_p(int(comm)))
         if rc != _cabi.OK:
             raise RuntimeError(f"b200disort_allreduce_band failed: {_cabi.strerror(rc)}")
@@ -360,9 +382,12 @@ class Disort:
 
     def reduce_band(self, flx, weights):
         """bflx(ncol, nlev, 2) = sum_n weights[n] flx[n] on the device (examples/amars_lw.cpp:88)."""
+        if not flx.is_cuda or flx.device != self.device:
+            raise ValueError("reduce_band: flx must be a CUDA tensor on the solver's device")
         w = weights.to(device=self.device, dtype=torch.float64).contiguous()
         out = torch.empty(flx.shape[1:], dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
+            self._use_current_stream()
             rc = self._lib.b200disort_reduce_band(self._h, flx.contiguous().data_ptr(), w.data_ptr(), out.data_ptr())
         if rc != _cabi.OK:
             raise RuntimeError(_cabi.strerror(rc))

@@ -200,6 +200,13 @@ def band_optics(attenuations, dz):
     """Mix attenuator outputs into the solver's input (examples/amars_sw.cpp:262-273):
     prop = sum_a att_a;  prop[..., 0] *= dz;  prop[..., 1] /= summed extinction.  dz: (nlyr,) or (nlyr, 1)."""
     atts = [a.contiguous() for a in attenuations]
+    if not atts:
+        raise ValueError("band_optics: no attenuator outputs")
+    for a in atts:  # raw pointers go to the kernel: every output must be a float64 CUDA tensor of the same leading shape
+        if not (a.is_cuda and a.dtype == torch.float64 and a.dim() == 4):
+            raise TypeError("band_optics: attenuator outputs must be 4-D float64 CUDA tensors (nwave, ncol, nlyr, nprop)")
+        if a.device != atts[0].device or tuple(a.shape[:3]) != tuple(atts[0].shape[:3]):
+            raise ValueError("band_optics: attenuator outputs must share their device and (nwave, ncol, nlyr)")
     nwave, ncol, nlyr, _ = atts[0].shape
     nprop = max(a.shape[3] for a in atts)
     dev = atts[0].device
