@@ -50,7 +50,8 @@ DEFAULT_NWAVE = {"amars_lw": 32, "amars_sw": 500, "lbl": 100000, "gcm": 32}
 DEFAULT_NLYR = {"amars_lw": 80, "amars_sw": 40, "lbl": 40, "gcm": 60}
 GCM_SEED_COLS = 2048  # the full-size GCM batch tiles a seeded block of this many columns (18 GB of inputs)
 TRAFFIC = os.path.join(ROOT, "profiles", "r02", "traffic.json")
-HASHED = ["pyharp_b200/csrc/disort_solver_body.inc", "pyharp_b200/csrc/disort_device.cuh",
+HASHED = ["pyharp_b200/csrc/disort_solver_body.inc", "pyharp_b200/csrc/disort_layer_ops.inc",
+          "pyharp_b200/csrc/disort_adding_step.inc", "pyharp_b200/csrc/disort_device.cuh",
           "pyharp_b200/csrc/flux_inst.cu", "pyharp_b200/workloads.py"]
 
 

@@ -118,6 +118,11 @@ int b200disort_solve_host(b200disort_handle* h, const double* prop, int nprop,
                           const b200disort_bc* bc, const double* temf, double* flx,
                           double* uu, int32_t* status);
 
+/* Flux-only batches of at most `max_solves` solves run on the warp-per-solve form of the flux kernel (lanes take the
+ * layers of a solve: per-call latency 1.6-1.9x lower for pyharp's own 500 x 1 / G x 1 calls); larger ones on the
+ * thread-per-solve form.  -1 restores the default (one resident wave of warps), 0 disables the warp form. */
+int b200disort_set_warp_solve_max(b200disort_handle* h, long max_solves);
+
 /* Synchronise and count non-zero status words of a device status array. */
 int b200disort_check_status(b200disort_handle* h, const int32_t* status, int* n_bad);
 

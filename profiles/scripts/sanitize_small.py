@@ -42,3 +42,30 @@ OP.band_optics([a], torch.ones(a.shape[2], dtype=torch.float64))
 OP.layer2level(torch.rand(4, 9, dtype=torch.float64, device=dev) + 1.0)
 print("opacity ok")
 torch.cuda.synchronize()
+
+# round 2: the band-level call (fused optics, fused band integration with L2 reductions, warp-reduced form with
+# replicas, chunked host entry, heating rate) and the solver-level fused band integration
+from pyharp_b200 import RadiationBand, RadiationBandOptions  # noqa: E402
+bw = W.make_band("amars_lw", nwave=12, ncol=37, nlyr=24)
+band = W.band_of(bw)
+band.options.host_chunk_cols(8)
+band = RadiationBand(band.options, nspecies=2)
+f = torch.from_numpy
+rho = bw.pres / (188.9 * bw.temp)
+for d in ("cpu", dev):
+    mv = lambda a: f(a).to(d)
+    out, dT = band.forward_band(mv(bw.conc), mv(bw.dz), {k: mv(v) for k, v in bw.bc.items()}, {"pres": mv(bw.pres), "temp": mv(bw.temp)},
+                                rho=mv(rho), cp=844.0)
+    assert bool(torch.isfinite(out).all()) and bool(torch.isfinite(dT).all())
+flx = band.forward(f(bw.conc).to(dev), f(bw.dz).to(dev), {k: f(v).to(dev) for k, v in bw.bc.items()},
+                   {"pres": f(bw.pres).to(dev), "temp": f(bw.temp).to(dev)})
+print("band ok", tuple(out.shape), tuple(flx.shape))
+for name, kw in (("lbl", dict(nwave=500, ncol=1, nlyr=9)), ("lbl", dict(nwave=200, ncol=4, nlyr=9)), ("amars_lw", dict(nwave=8, ncol=40, nlyr=9)),
+                 ("gcm", dict(nwave=3, ncol=40, nlyr=5))):
+    wl = W.make(name, **kw)
+    ds = Disort(wl.options())
+    t = lambda a: None if a is None else torch.from_numpy(a).to(dev)
+    b = ds.forward_band(t(wl.prop), {k: t(v) for k, v in wl.bc.items()}, t(wl.temf), torch.ones(wl.shape[0], dtype=torch.float64))
+    assert bool(torch.isfinite(b).all())
+    print("solve_band", name, kw["ncol"], "ok")
+torch.cuda.synchronize()

@@ -311,6 +311,39 @@ static int ring_end(b200disort_handle* h, cudaStream_t stream) {
 int b200::launch_flux(b200disort_handle* h, SolveParams& p, cudaStream_t stream, double** ws, size_t* ws_bytes,
                       bool timed) {
   const FluxInst* inst = h->inst;
+  // Batches far below one resident wave (pyharp's own calls: 500 x 1, G x 1 solves): the warp-per-solve form, whose
+  // lanes take the layers of a solve -- a thread-per-solve launch would occupy a handful of SMs for as long as one
+  // thread needs to walk the column.  One call of it lasts ~0.55x as long (profiles/r02/sweeps.md, e32), so it is used
+  // up to ONE resident wave of warps (148 SMs x 8 warps = 1184 solves); B200DISORT_WARP_SOLVE_MAX / the handle's
+  // warp_solve_max override the threshold (0 = never).
+  if (inst->launch_warp) {
+    static const long env_max = std::getenv("B200DISORT_WARP_SOLVE_MAX") ? std::atol(std::getenv("B200DISORT_WARP_SOLVE_MAX")) : -1;
+    if (h->occ_warp == 0) {
+      int occ = 0;
+      CU_TRY(inst->warp_occupancy(128, &occ));
+      h->occ_warp = occ < 1 ? 1 : occ;
+    }
+    const long wave_warps = (long)h->sm_count * h->occ_warp * 4;
+    const long max_solves = h->warp_solve_max >= 0 ? h->warp_solve_max : env_max >= 0 ? env_max : wave_warps;
+    if (p.nlocal <= max_solves) {
+      const long grid = std::min<long>((p.nlocal + 3) / 4, (long)h->sm_count * h->occ_warp);
+      const size_t need = (size_t)grid * 4 * inst->warp_scratch(p.nlyr) * sizeof(double);
+      int rc = ensure_dev(ws, ws_bytes, need);
+      if (rc != B200DISORT_OK) return rc;
+      if (timed) {
+        rc = ring_begin(h, stream);
+        if (rc != B200DISORT_OK) return rc;
+      }
+      CU_TRY(inst->launch_warp(p, (unsigned)grid, 128, stream, *ws));
+      if (timed) {
+        rc = ring_end(h, stream);
+        if (rc != B200DISORT_OK) return rc;
+      }
+      h->stats.kernel_launches += 1;
+      h->stats.workspace_bytes = *ws_bytes;
+      return B200DISORT_OK;
+    }
+  }
   // tuning knobs (profiling only): B200DISORT_BLOCK = threads per CTA (<= 128), B200DISORT_CTAS_PER_SM caps residency
   static const int env_block = std::getenv("B200DISORT_BLOCK") ? std::atoi(std::getenv("B200DISORT_BLOCK")) : 0;
   static const int env_ctas = std::getenv("B200DISORT_CTAS_PER_SM") ? std::atoi(std::getenv("B200DISORT_CTAS_PER_SM")) : 0;
@@ -493,6 +526,12 @@ extern "C" int b200disort_set_stream(b200disort_handle* h, void* stream) {
   CU_TRY(cudaStreamSynchronize(h->stream));
   h->stream = (cudaStream_t)stream;
   h->cfg.stream = stream;
+  return B200DISORT_OK;
+}
+
+extern "C" int b200disort_set_warp_solve_max(b200disort_handle* h, long max_solves) {
+  if (!h) return B200DISORT_ERR_INVALID;
+  h->warp_solve_max = max_solves;
   return B200DISORT_OK;
 }
 

@@ -16,6 +16,8 @@ struct b200disort_handle {
   cudaStream_t stream = nullptr;
   int sm_count = 0;
   int occ = 0;  // resident CTAs per SM of the flux kernel
+  int occ_warp = 0;  // ... of its warp-per-solve form
+  long warp_solve_max = -1;  // largest batch sent to the warp-per-solve form (-1: one wave of warps)
   std::vector<double> user_tau, user_mu, user_phi, wave_lower, wave_upper;
   // device-side constants
   double *d_wlo = nullptr, *d_whi = nullptr, *d_blo = nullptr, *d_bhi = nullptr;

@@ -542,6 +542,20 @@ struct YRef<NN, true> {
 };
 #endif
 
+// Warp-per-solve form (disort_solver_body.inc, last section): per-layer hand-over record
+//   Rl | Tl (packed symmetric) | s+ | s- | expbea at the layer top | at the bottom
+template <int NN>
+constexpr int kOpsDoubles = NN * (NN + 1) + 2 * NN + 2;
+// ... and what every phase of a solve needs of its boundary conditions
+template <int NN>
+struct SolveCommon {
+  double umu0, rmu0, fbeam, albedo, fisot, tplank, bplank;
+  double y0[2 * NN];
+  const double* pk;  // Planck emission per level, DISORT order (null without thermal sources)
+  int n, j, st;
+  bool beam, planck;
+};
+
 // fully unrolled instantiation (small nn: registers)
 #define B200_UNROLL _Pragma("unroll")
 #define B200_FN(name) name##_u
@@ -564,6 +578,12 @@ B200_HD void solve_flux_one(const SolveParams& p, const QT& qt, long s, long tid
 #endif
   if constexpr (NN <= B200_UNROLL_MAX_NN) solve_flux_one_u<NN, NOMOM, BAND>(p, qt, s, tid, active, ring_pos, pend, wshalf);
   else solve_flux_one_r<NN, NOMOM, BAND>(p, qt, s, tid, active, ring_pos, pend, wshalf);
+}
+
+// layer-wise (warp-per-solve) order on one thread: host simulator entry
+template <int NN, bool NOMOM = false, int BAND = 0, typename QT>
+B200_HD void solve_flux_layerwise(const SolveParams& p, const QT& qt, long s, double* opsbuf, double* recbuf) {
+  solve_flux_layerwise_u<NN, NOMOM, BAND>(p, qt, s, opsbuf, recbuf);
 }
 
 // finishes a pending (carried) back sweep after a thread's last solve

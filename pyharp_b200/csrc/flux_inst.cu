@@ -92,6 +92,82 @@ __global__ void __launch_bounds__(B200_MAX_THREADS, B200_MIN_BLOCKS) disort_flux
   }
 }
 
+// ---------------------------------------------------------------------------
+// Warp-per-solve kernel (see the block comment in disort_solver_body.inc): lanes take the layers of one solve up to the
+// layer operators, lane 0 runs the adding recursion and the back sweep.  Scratch per warp: nlyr hand-over records +
+// nlyr back-sweep records (global memory, L1/L2-resident: written and read by the same warp within microseconds).
+// ---------------------------------------------------------------------------
+#if B200_NN <= 4
+#define B200_HAVE_WARP 1
+#else
+#define B200_HAVE_WARP 0
+#endif
+#if B200_HAVE_WARP
+template <bool NOMOM, int BAND>
+__global__ void __launch_bounds__(128, 1) disort_flux_warp_kernel(SolveParams p, double* scratch) {
+  constexpr int NN = B200_NN;
+  constexpr int NOPS = kOpsDoubles<NN>;
+  const int lane = (int)(threadIdx.x & 31);
+  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  const int nlyr = p.nlyr;
+  double* opsbuf = scratch + warp * ((long)nlyr * (NOPS + kNsave));
+  double* recbuf = opsbuf + (long)nlyr * NOPS;
+  for (long s = warp; s < p.nlocal; s += nwarps) {
+    SolveCommon<NN> cm;
+    solve_common_u<NN>(p, c_qt, s, cm);
+    const double* pr = p.prop + s * nlyr * p.nprop;
+    int ncut = nlyr, st = cm.st;
+    double carry_t = 0.0, carry_a = 0.0;
+    bool cut = false;
+    for (int base = 0; base < nlyr && !cut; base += 32) {
+      const int lc = base + lane;
+      double dtp = 0.0, dabs = 0.0;
+      if (lc < nlyr) layer_depths_u<NN, NOMOM>(p, pr, lc, dtp, dabs);
+      double it = dtp, ia = dabs;  // inclusive prefix sums over the 32 layers of this round
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double a = __shfl_up_sync(0xffffffffu, it, o), b = __shfl_up_sync(0xffffffffu, ia, o);
+        if (lane >= o) { it += a; ia += b; }
+      }
+      const double taup = carry_t + (it - dtp), abefore = carry_a + (ia - dabs);
+      // c_disort_set: the medium is cut at the first layer above which the absorption optical depth reaches 10
+      const unsigned m = __ballot_sync(0xffffffffu, !cm.planck && nlyr > 1 && lc < nlyr && abefore >= 10.0);
+      if (m) { ncut = base + __ffs(m) - 1; cut = true; }
+      if (lc < min(ncut, nlyr)) st = status_merge_u(st, layer_ops_u<NN, NOMOM>(p, c_qt, cm, pr, lc, taup, opsbuf + (long)lc * NOPS));
+      carry_t += __shfl_sync(0xffffffffu, it, 31);
+      carry_a += __shfl_sync(0xffffffffu, ia, 31);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) st = status_merge_u(st, __shfl_xor_sync(0xffffffffu, st, o));
+    const bool lyrcut = cut || (!cm.planck && nlyr > 1 && carry_a >= 10.0);
+    __syncwarp();  // the hand-over records of all lanes are visible to lane 0
+    if (lane == 0) adding_sweep_u<NN, BAND>(p, c_qt, cm, s, pr, ncut, lyrcut, st, opsbuf, recbuf);
+    __syncwarp();  // ... and consumed before the next solve overwrites them
+  }
+}
+
+long warp_scratch(int nlyr) { return (long)nlyr * (kOpsDoubles<B200_NN> + kNsave); }
+
+cudaError_t warp_occupancy(int block, int* blocks_per_sm) {
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, disort_flux_warp_kernel<false, 0>, block, 0);
+}
+
+cudaError_t launch_warp(const SolveParams& p, unsigned grid, int block, cudaStream_t stream, double* scratch) {
+  const bool band = p.bflx_t != nullptr;
+#if B200_HAVE_NOMOM
+  if (p.nprop <= 2) {
+    if (band) disort_flux_warp_kernel<true, 1><<<grid, block, 0, stream>>>(p, scratch);
+    else disort_flux_warp_kernel<true, 0><<<grid, block, 0, stream>>>(p, scratch);
+  } else
+#endif
+  {
+    if (band) disort_flux_warp_kernel<false, 1><<<grid, block, 0, stream>>>(p, scratch);
+    else disort_flux_warp_kernel<false, 0><<<grid, block, 0, stream>>>(p, scratch);
+  }
+  return cudaGetLastError();
+}
+#endif
+
 cudaError_t upload_tables(const QuadTables* qt) { return cudaMemcpyToSymbol(c_qt, qt, sizeof(QuadTables)); }
 
 // dynamic shared memory per CTA: the parked stack state (Ra packed symmetric + da) of every thread
@@ -159,7 +235,13 @@ cudaError_t launch(const SolveParams& p, unsigned grid, int block, cudaStream_t 
   return cudaGetLastError();
 }
 
-const FluxInst kInst = {B200_NN, B200_NN * B200_NN + 2 * B200_NN + 1, B200_MAX_THREADS, kCarryBack<B200_NN> ? 2 : 1, upload_tables, occupancy, launch};
+#if B200_HAVE_WARP
+const FluxInst kInst = {B200_NN, B200_NN * B200_NN + 2 * B200_NN + 1, B200_MAX_THREADS, kCarryBack<B200_NN> ? 2 : 1, upload_tables, occupancy, launch,
+                        warp_scratch, warp_occupancy, launch_warp};
+#else
+const FluxInst kInst = {B200_NN, B200_NN * B200_NN + 2 * B200_NN + 1, B200_MAX_THREADS, kCarryBack<B200_NN> ? 2 : 1, upload_tables, occupancy, launch,
+                        nullptr, nullptr, nullptr};
+#endif
 
 }  // namespace
 

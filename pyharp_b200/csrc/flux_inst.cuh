@@ -16,6 +16,11 @@ struct FluxInst {
   cudaError_t (*upload_tables)(const QuadTables*);
   cudaError_t (*occupancy)(int block, int* blocks_per_sm);
   cudaError_t (*launch)(const SolveParams&, unsigned grid, int block, cudaStream_t);
+  // warp-per-solve form for batches far below one resident wave (null where it is not instantiated): doubles of
+  // scratch per warp, resident CTAs per SM, launch
+  long (*warp_scratch)(int nlyr);
+  cudaError_t (*warp_occupancy)(int block, int* blocks_per_sm);
+  cudaError_t (*launch_warp)(const SolveParams&, unsigned grid, int block, cudaStream_t, double* scratch);
 };
 
 #define B200_DECL_INST(NN) const FluxInst* flux_inst_##NN();

@@ -206,6 +206,13 @@ class Disort:
             self._lib.b200disort_destroy(h)
             self._h = None
 
+    def set_warp_solve_max(self, max_solves):
+        """Largest flux-only batch that runs on the warp-per-solve form of the kernel (-1: default, 0: never)."""
+        rc = self._lib.b200disort_set_warp_solve_max(self._h, int(max_solves))
+        if rc != _cabi.OK:
+            raise RuntimeError(_cabi.strerror(rc))
+        return self
+
     def ds(self, n=0, j=0):
         return self.options.ds()
 

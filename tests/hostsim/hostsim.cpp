@@ -11,10 +11,30 @@
 
 using namespace b200;
 
+static int g_layerwise = 0;  // hostsim_set_layerwise: run the warp-per-solve order (layer operators first, then the sweep)
+
 template <int NN>
 static void run(SolveParams& p, const QuadTables& qt) {
   const long nsolve = (long)p.nwave * p.ncol;
   constexpr int NSAVE = NN * NN + 2 * NN + 1;
+  if (g_layerwise) {
+    if constexpr (NN <= 4) {  // (the warp-per-solve kernel is instantiated for nstr <= 8)
+      std::vector<double> ops((size_t)p.nlyr * kOpsDoubles<NN>), rec((size_t)p.nlyr * NSAVE);
+      p.s0 = 0;
+      p.nlocal = nsolve;
+      const bool band = p.bflx_t != nullptr;
+      for (long s = 0; s < nsolve; ++s) {
+        if (p.nprop <= 2) {
+          if (band) solve_flux_layerwise<NN, true, 1>(p, qt, s, ops.data(), rec.data());
+          else solve_flux_layerwise<NN, true, 0>(p, qt, s, ops.data(), rec.data());
+        } else {
+          if (band) solve_flux_layerwise<NN, false, 1>(p, qt, s, ops.data(), rec.data());
+          else solve_flux_layerwise<NN, false, 0>(p, qt, s, ops.data(), rec.data());
+        }
+      }
+      return;
+    }
+  }
   // same driver structure as disort_flux_kernel (flux_inst.cu): where the kernel carries the back sweep of one
   // solve into the thread's next solve, so does this loop (alternating workspace halves, drain at the end)
   const size_t half = (size_t)p.nlyr * NSAVE;
@@ -42,6 +62,8 @@ static void run(SolveParams& p, const QuadTables& qt) {
     else drain_back_sweep<NN, 0>(p, pend, qt, 0, ring_pos);
   }
 }
+
+extern "C" void hostsim_set_layerwise(int on) { g_layerwise = on; }
 
 extern "C" int hostsim_flux(int nwave, int ncol, int nlyr, int nstr, int nprop, unsigned flags,
                             const double* prop, const double* umu0, const double* fbeam,

@@ -16,6 +16,8 @@ def _lib():
             os.path.join(_D, "..", "..", "pyharp_b200", "csrc", "disort_device.cuh"),
             os.path.join(_D, "..", "..", "pyharp_b200", "csrc", "host_tables.hpp"),
             os.path.join(_D, "..", "..", "pyharp_b200", "csrc", "disort_solver_body.inc"),
+            os.path.join(_D, "..", "..", "pyharp_b200", "csrc", "disort_layer_ops.inc"),
+            os.path.join(_D, "..", "..", "pyharp_b200", "csrc", "disort_adding_step.inc"),
             os.path.join(_D, "..", "..", "pyharp_b200", "csrc", "intensity_device.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, srcs[0]])
@@ -32,7 +34,8 @@ def _lib():
 _L = None
 
 
-def flux(prop, bc=None, temf=None, *, nstr, flags, wave_lower=None, wave_upper=None, weights=None, bc_bcast=False):
+def flux(prop, bc=None, temf=None, *, nstr, flags, wave_lower=None, wave_upper=None, weights=None, bc_bcast=False,
+         layerwise=False):
     """Flux kernel body on the host.  With `weights` (nwave) the BAND instantiation runs instead (fused band
     integration): returns (bflx (ncol, nlyr+1, 2), status).  bc_bcast: boundary fields are (ncol) arrays."""
     global _L
@@ -58,6 +61,7 @@ def flux(prop, bc=None, temf=None, *, nstr, flags, wave_lower=None, wave_upper=N
     st = np.zeros((nwave, ncol), dtype=np.int32)
     sh = (ncol,) if bc_bcast else (nwave, ncol)
     bflx_t = None if weights is None else np.zeros((nlyr + 1, 2, ncol))
+    _L.hostsim_set_layerwise(int(layerwise))  # the order of the warp-per-solve kernel (nstr <= 8)
     rc = _L.hostsim_flux(nwave, ncol, nlyr, nstr, nprop, flags, P(prop),
                          P(bc.get("umu0"), sh), P(bc.get("fbeam"), sh), P(bc.get("albedo"), sh),
                          P(bc.get("btemp"), sh), P(bc.get("ttemp"), sh), P(bc.get("temis"), sh),

@@ -37,10 +37,15 @@ CASES = [
 
 @pytest.mark.parametrize("name,kw", CASES, ids=[f"{n}-{i}" for i, (n, _) in enumerate(CASES)])
 @pytest.mark.parametrize("where", ["host", "device"])
-def test_flux_parity(cuda_device, name, kw, where):
+@pytest.mark.parametrize("form", ["thread_per_solve", "warp_per_solve"])
+def test_flux_parity(cuda_device, name, kw, where, form):
+    """Both forms of the flux kernel: small batches default to the warp-per-solve form (nstr <= 8), which is forced off /
+    on here so that each case runs on each form that exists for its stream count."""
     wl = W.make(name, **kw)
+    if form == "warp_per_solve" and wl.nstr > 8:
+        pytest.skip("the warp-per-solve form is instantiated for nstr <= 8")
     ref = _oracle(wl)
-    ds = Disort(wl.options())
+    ds = Disort(wl.options()).set_warp_solve_max(0 if form == "thread_per_solve" else 1 << 30)
     dev = "cpu" if where == "host" else cuda_device
     t = lambda a: None if a is None else torch.from_numpy(a).to(dev)
     flx = ds.forward(t(wl.prop), {k: t(v) for k, v in wl.bc.items()}, t(wl.temf))
@@ -90,11 +95,14 @@ import golden_lib as G  # noqa: E402
 
 
 @pytest.mark.parametrize("name", G.NAMES)
-def test_golden_fixtures(cuda_device, name):
+@pytest.mark.parametrize("form", ["thread_per_solve", "warp_per_solve"])
+def test_golden_fixtures(cuda_device, name, form):
     """Committed fixtures: extended-precision oracle, independent numpy solve, and (amars_sw_real) the real
-    inputs of the reference's examples/amars_sw.cpp."""
+    inputs of the reference's examples/amars_sw.cpp; on both forms of the flux kernel."""
     wl, ld, ind, valid = G.load(name)
-    ds = Disort(wl.options())
+    if form == "warp_per_solve" and wl.nstr > 8:
+        pytest.skip("the warp-per-solve form is instantiated for nstr <= 8")
+    ds = Disort(wl.options()).set_warp_solve_max(0 if form == "thread_per_solve" else 1 << 30)
     t = lambda a: None if a is None else torch.from_numpy(a).to(cuda_device)
     flx = ds.forward(t(wl.prop), {k: t(v) for k, v in wl.bc.items()}, t(wl.temf)).cpu().numpy()
     G.check(flx, ld, RTOL)  # fluxes and per-layer net-flux divergence
@@ -127,8 +135,9 @@ def test_every_stream_count(cuda_device, nstr, thermal):
         kw = dict(wave_lower=np.array([100.0, 600.0, 1500.0]), wave_upper=np.array([600.0, 1500.0, 1510.0]))
     wl = W.Workload("streams", nstr, tokens, prop, bc, temf, kw.get("wave_lower"), kw.get("wave_upper"))
     ref = _oracle(wl)
-    ds = Disort(wl.options())
     t = lambda a: None if a is None else torch.from_numpy(a).to(cuda_device)
-    flx = ds.forward(t(prop), {k: t(v) for k, v in bc.items()}, t(temf)).cpu().numpy()
-    assert _relerr(flx, ref) < RTOL
-    assert G.diverr(flx, ref) < RTOL
+    for limit in ((0, 1 << 30) if nstr <= 8 else (0,)):  # thread-per-solve, then (where it exists) warp-per-solve
+        ds = Disort(wl.options()).set_warp_solve_max(limit)
+        flx = ds.forward(t(prop), {k: t(v) for k, v in bc.items()}, t(temf)).cpu().numpy()
+        assert _relerr(flx, ref) < RTOL
+        assert G.diverr(flx, ref) < RTOL

@@ -19,6 +19,23 @@ def _sim(wl):
 
 
 @pytest.mark.parametrize("name", G.NAMES)
+def test_hostsim_layerwise_order(name):
+    """The order of the warp-per-solve kernel (layer operators first, then one serial adding sweep; nstr <= 8)."""
+    wl, ld, ind, valid = G.load(name)
+    if wl.nstr > 8:
+        pytest.skip("warp-per-solve form: nstr <= 8")
+    flx, st = H.flux(wl.prop, wl.bc, wl.temf, nstr=wl.nstr, flags=wl.flags, wave_lower=wl.wave_lower,
+                     wave_upper=wl.wave_upper, layerwise=True)
+    assert not st.any()
+    G.check(flx, ld, RTOL)
+    w = np.linspace(0.5, 1.5, wl.shape[0])
+    bflx, st = H.flux(wl.prop, wl.bc, wl.temf, nstr=wl.nstr, flags=wl.flags, wave_lower=wl.wave_lower,
+                      wave_upper=wl.wave_upper, layerwise=True, weights=w)
+    ref = (flx * w[:, None, None, None]).sum(0)
+    assert np.max(np.abs(bflx - ref)) <= 1e-14 * np.max(np.abs(ref))
+
+
+@pytest.mark.parametrize("name", G.NAMES)
 def test_hostsim_vs_golden(name):
     wl, ld, ind, valid = G.load(name)
     flx, st = _sim(wl)
