@@ -209,6 +209,152 @@ __global__ void __launch_bounds__(256, MINB) band_optics_fused_kernel(const Band
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Tile form of the fused optics kernel (the default when every RFM attenuator sits on its table's own spectral grid):
+// a warp owns 32 (column, layer) points x all spectral points.
+//   phase 1  lane = point: ln p, reference temperature, bracketing rows and blend weights of every attenuator
+//            (harp::locate on axes in shared memory) -> a per-warp record in shared memory;
+//   phase 2  lane = spectral point: for each of the 32 points the record is read as a broadcast and the four table
+//            corners are ONE coalesced 256-byte load each (table transposed to (ln p, dT, wave)) -- the thread-per-point
+//            form paid an L1 wavefront per lane for every gather (l1tex 68-88 % busy, FP64 pipe 10-19 %);
+//   phase 3  the 32 x 32 (wave, point) tile goes through shared memory so that prop (wave, point) is written with
+//            coalesced 256-byte stores.
+// Same arithmetic, statement by statement, as the hoisted-weight path of band_optics_fused_kernel.
+// ---------------------------------------------------------------------------
+constexpr int kTileWarps = 4;
+#ifndef B200_TILE_ILP
+#define B200_TILE_ILP 4
+#endif
+constexpr int kPtIlp = B200_TILE_ILP;  // points of a tile evaluated side by side (independent exp chains)
+struct TileRec {      // one (point, attenuator)
+  int o11, o12, o21, o22;          // element offsets of the four (ln p, dT) corners in the transposed table
+  double f11, f12, f21, f22, cs;   // their weights; 1e-3 conc (RFM) or conc (aerosol)
+};
+
+__global__ void __launch_bounds__(kTileWarps * 32) band_optics_tile_kernel(const BandOpticsParams P, long ntile) {
+  extern __shared__ double b200_axes[];
+  for (int a = 0; a < P.natt; ++a) {
+    const DevAtt& A = P.att[a];
+    if (A.type != B200_ATT_RFM || A.same_axes) continue;
+    double* s = b200_axes + A.sm_off;
+    const int n = P.nlyr;
+    for (int k = threadIdx.x; k < 2 * n + A.n1 + A.n2; k += blockDim.x)
+      s[k] = k < n ? A.klnp[k] : k < 2 * n ? A.ktemp[k - n] : A.kaxis[A.n0 + (k - 2 * n)];
+  }
+  __syncthreads();
+  const int lane = (int)(threadIdx.x & 31), wib = (int)(threadIdx.x >> 5);
+  // per-warp shared memory behind the axes: records [natt][32], dz [32], tile(s) [nprop][32][33]
+  const int rec_doubles = (int)(sizeof(TileRec) / sizeof(double));
+  const int per_warp = P.natt * 32 * rec_doubles + 32 + P.nprop * 32 * 33;
+  double* wsm = b200_axes + ((P.sm_doubles + 3) & ~3) + (long)wib * per_warp;
+  TileRec* recs = reinterpret_cast<TileRec*>(wsm);
+  double* dzs = wsm + P.natt * 32 * rec_doubles;
+  double* tile = dzs + 32;
+  for (long t = (long)blockIdx.x * kTileWarps + wib; t < ntile; t += (long)gridDim.x * kTileWarps) {
+    const long i0 = t * 32;
+    const long i = i0 + lane;
+    const bool valid = i < P.npoint;
+    // ---- phase 1: this lane's point
+    {
+      double lnp = 0.0, dT = 0.0, wp1 = 0.0, wp2 = 0.0, wt1 = 0.0, wt2 = 0.0;
+      int ip1 = 0, ip2 = 0, it1 = 0, it2 = 0;
+      const long ii = valid ? i : P.npoint - 1;
+      for (int a = 0; a < P.natt; ++a) {
+        const DevAtt& A = P.att[a];
+        TileRec r;
+        const double cv = P.conc[ii * P.nspecies + A.sid];
+        if (A.type == B200_ATT_AEROSOL) {
+          r.o11 = r.o12 = r.o21 = r.o22 = 0;
+          r.f11 = r.f12 = r.f21 = r.f22 = 0.0;
+          r.cs = cv;
+        } else {
+          const double* sax = b200_axes + A.sm_off;
+          if (!A.same_axes) {
+            lnp = log(P.pres[ii]);
+            Dims rd{};
+            rd.len[0] = P.nlyr; rd.stride[0] = 1; rd.axis_off[0] = 0;
+            double tref;
+            interpn_dev<1, 1>(&tref, &lnp, sax + P.nlyr, sax, rd, 0);
+            dT = __dsub_rn(P.temp[ii], tref);
+            bracket_dev(sax + 2 * P.nlyr, A.n1, lnp, ip1, ip2, wp1, wp2);
+            bracket_dev(sax + 2 * P.nlyr + A.n1, A.n2, dT, it1, it2, wt1, wt2);
+          }
+          r.o11 = (ip1 * A.n2 + it1) * A.n0; r.o12 = (ip1 * A.n2 + it2) * A.n0;
+          r.o21 = (ip2 * A.n2 + it1) * A.n0; r.o22 = (ip2 * A.n2 + it2) * A.n0;
+          r.f11 = wp1 * wt1; r.f12 = wp1 * wt2; r.f21 = wp2 * wt1; r.f22 = wp2 * wt2;
+          r.cs = 1.0e-3 * cv;
+        }
+        recs[a * 32 + lane] = r;
+      }
+      dzs[lane] = P.dz ? P.dz[(int)(ii % P.nlyr)] : 1.0;
+    }
+    __syncwarp();
+    const int npt = (int)min((long)32, P.npoint - i0);
+    for (int wb = 0; wb < P.nwave; wb += 32) {
+      const int wv = wb + lane;
+      const bool wok = wv < P.nwave;
+      const int wc = wok ? wv : P.nwave - 1;
+      // ---- phase 2: this lane's spectral point, every point of the tile -- kPtIlp points at a time, so that as many
+      //      independent exp() chains per attenuator are in flight (the kernel is bound by their latency)
+      for (int p0 = 0; p0 < npt; p0 += kPtIlp) {
+        double ext[kPtIlp], sse[kPtIlp];
+#pragma unroll
+        for (int u = 0; u < kPtIlp; ++u) { ext[u] = 0.0; sse[u] = 0.0; }
+        for (int a = 0; a < P.natt; ++a) {
+          const DevAtt& A = P.att[a];
+          if (A.type == B200_ATT_AEROSOL) {
+            const double k0 = A.kw[2 * wc], k1 = A.kw[2 * wc + 1];
+#pragma unroll
+            for (int u = 0; u < kPtIlp; ++u) {
+              const double e = __dmul_rn(k0, recs[a * 32 + min(p0 + u, 31)].cs);
+              ext[u] = __dadd_rn(ext[u], e);
+              sse[u] = __dadd_rn(sse[u], __dmul_rn(k1, e));
+            }
+          } else {
+            const double* T = A.kdata_t + wc;
+            double v[kPtIlp];
+#pragma unroll
+            for (int u = 0; u < kPtIlp; ++u) {
+              const TileRec& r = recs[a * 32 + min(p0 + u, 31)];
+              v[u] = fma(r.f11, T[r.o11], fma(r.f12, T[r.o12], fma(r.f21, T[r.o21], r.f22 * T[r.o22])));
+            }
+#pragma unroll
+            for (int u = 0; u < kPtIlp; ++u) ext[u] = fma(exp(v[u]), recs[a * 32 + min(p0 + u, 31)].cs, ext[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kPtIlp; ++u) {
+          const int pt = p0 + u;
+          if (pt < npt) {
+            const double dzl = dzs[pt];
+            const double tau = __dmul_rn(ext[u], dzl);
+            tile[lane * 33 + pt] = tau;
+            if (P.nprop > 1) {
+              double ssa;
+              if (P.eps > 0.0) ssa = __ddiv_rn(sse[u], __dadd_rn(ext[u], P.eps));
+              else ssa = (tau == 0.0) ? 0.0 : __ddiv_rn(__dmul_rn(sse[u], dzl), tau);
+              tile[32 * 33 + lane * 33 + pt] = fmin(ssa, 1.0);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      // ---- phase 3: rows of the tile (one spectral point each) -> prop, lanes = points
+      const int nwv = min(32, P.nwave - wb);
+      if (valid) {
+        if (P.nprop == 1) {
+          for (int r = 0; r < nwv; ++r) P.prop[(long)(wb + r) * P.npoint + i] = tile[r * 33 + lane];
+        } else {
+          double2* o = reinterpret_cast<double2*>(P.prop);
+          for (int r = 0; r < nwv; ++r) o[(long)(wb + r) * P.npoint + i] = make_double2(tile[r * 33 + lane], tile[32 * 33 + r * 33 + lane]);
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // (k_ext, ssa) of an aerosol table at every spectral point: harp::interpn<1> with nval = 2, once per band
 __global__ void aerosol_wave_kernel(const double* __restrict__ kwave, const double* __restrict__ kdata, int rows,
                                     const double* __restrict__ wave, int nwave, int is_wavenumber, double* __restrict__ kw) {
@@ -282,7 +428,7 @@ struct b200_band {
   int nwave = 0, ncol = 0, nlyr = 0, nlev = 0, nspecies = 0, nprop = 1, natt = 0;
   int l2l_order = 1, l2l_blower = 0, l2l_bupper = 1, exact = 0, host_chunk_cols = 0;
   double eps = 0.0;
-  bool planck = false, need_pres = false;
+  bool planck = false, need_pres = false, tile_smem_set = false;
   DevAtt att[B200_BAND_MAX_ATT];
   std::vector<void*> owned;  // device tables
   double* d_weights = nullptr;
@@ -363,6 +509,27 @@ int launch_optics(b200_band* b, cudaStream_t st, int cc, const double* conc, con
   }
   P.sm_doubles = smd;
   const size_t sm = (size_t)smd * sizeof(double);
+  // tile form: hoisted weights, every RFM attenuator on its table's own spectral grid
+  {
+    static const int env_tile = std::getenv("B200_BAND_TILE") ? std::atoi(std::getenv("B200_BAND_TILE")) : 1;  // profiling knob
+    bool ok = env_tile != 0 && !b->exact && P.npoint >= 32;
+    for (int a = 0; a < b->natt; ++a)
+      if (P.att[a].type == B200_ATT_RFM && (!P.att[a].on_grid || (long)P.att[a].n0 * P.att[a].n1 * P.att[a].n2 >= (1L << 31))) ok = false;
+    const int per_warp = b->natt * 32 * (int)(sizeof(TileRec) / sizeof(double)) + 32 + b->nprop * 32 * 33;
+    const size_t smt = ((size_t)((smd + 3) & ~3) + (size_t)kTileWarps * per_warp) * sizeof(double);
+    if (ok && smt <= 200 * 1024) {
+      if (smt > 48 * 1024 && !b->tile_smem_set) {
+        CU_TRY(cudaFuncSetAttribute(band_optics_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        b->tile_smem_set = true;
+      }
+      const long ntile = (P.npoint + 31) / 32;
+      const long grid = std::min<long>((ntile + kTileWarps - 1) / kTileWarps, (long)h->sm_count * 16);
+      band_optics_tile_kernel<<<(unsigned)grid, kTileWarps * 32, smt, st>>>(P, ntile);
+      CU_TRY(cudaGetLastError());
+      h->stats.kernel_launches += 1;
+      return B200DISORT_OK;
+    }
+  }
   // enough points to fill the machine with tiles of 8 spectral points per thread?  otherwise one per thread
   static const int env_wt = std::getenv("B200_BAND_WT") ? std::atoi(std::getenv("B200_BAND_WT")) : 0;  // profiling knob: 10 * WT + MINB
   const int sel = env_wt ? env_wt : (nwave >= 16 ? 162 : 82);
