@@ -57,6 +57,27 @@ def test_band_lw_against_reference_chain(cuda_device, lw, exact):
     assert band.stats()["solves_timed"] >= 1
 
 
+@pytest.mark.parametrize("shape", [dict(nwave=70, ncol=3, nlyr=17), dict(nwave=5, ncol=1, nlyr=33), dict(nwave=33, ncol=65, nlyr=9)],
+                         ids=["70x3x17", "5x1x33", "33x65x9"])
+def test_band_odd_shapes(cuda_device, shape):
+    """Ragged tiles of the optics kernel (spectral points not a multiple of 32, fewer than 32 points), one column
+    (warp-reduced band integration, warp-per-solve flux kernel), host and device entries."""
+    bw = W.make_band("amars_lw", variant=4, **shape)
+    prop_ref, _, flx_ref, bflx_ref = BC.lw_chain(bw)
+    band = W.band_of(bw)
+    t = lambda a: torch.from_numpy(a).to(cuda_device)
+    f = torch.from_numpy
+    op = {"pres": t(bw.pres), "temp": t(bw.temp)}
+    flx = band.forward(t(bw.conc), t(bw.dz), {k: t(v) for k, v in bw.bc.items()}, op).cpu().numpy()
+    np.testing.assert_allclose(band.shared["radiation/B1/optics"].cpu().numpy(), prop_ref, rtol=1e-12, atol=0)
+    scale = np.max(np.abs(flx_ref), axis=(2, 3), keepdims=True)
+    assert float(np.max(np.abs(flx - flx_ref) / scale)) < RTOL
+    for where in ("device", "host"):
+        mv = t if where == "device" else f
+        b = band.forward_band(mv(bw.conc), mv(bw.dz), {k: mv(v) for k, v in bw.bc.items()}, {"pres": mv(bw.pres), "temp": mv(bw.temp)})
+        assert _rel(b.cpu().numpy(), bflx_ref) < RTOL, where
+
+
 def test_band_host_chunks_and_heating_rate(cuda_device, lw):
     """Several chunks through the three slots (chunk = 8 columns of 37, last one ragged), heating rate output."""
     bw, (_, _, _, bflx_ref) = lw
