@@ -123,6 +123,12 @@ int b200disort_solve_host(b200disort_handle* h, const double* prop, int nprop,
  * thread-per-solve form.  -1 restores the default (one resident wave of warps), 0 disables the warp form. */
 int b200disort_set_warp_solve_max(b200disort_handle* h, long max_solves);
 
+/* Stream counts nstr >= 12: form of the flux solve.  1 = layer-split (the layer phase -- eigenproblem, particular
+ * solutions, reflection / transmission operators, cdisort's c_sol_eigen / c_upbeam / c_upisot -- as one thread per
+ * (solve, layer), then the adding recursion and the back sweep -- c_set_matrix / c_solve0 / c_fluxes -- as one thread per
+ * solve), 0 = one fused kernel, -1 = the default for the stream count.  No effect at nstr <= 8. */
+int b200disort_set_layer_split(b200disort_handle* h, int mode);
+
 /* Synchronise and count non-zero status words of a device status array. */
 int b200disort_check_status(b200disort_handle* h, const int32_t* status, int* n_bad);
 

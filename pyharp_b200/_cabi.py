@@ -57,7 +57,7 @@ ATT_RFM, ATT_AEROSOL = 1, 2
 
 EXPORTS = ("b200disort_create", "b200disort_solve", "b200disort_solve_host",
            "b200disort_check_status", "b200disort_get_rad", "b200disort_reduce_band",
-           "b200disort_get_stats", "b200disort_set_stream", "b200disort_set_warp_solve_max", "b200disort_fp64_peak", "b200disort_destroy",
+           "b200disort_get_stats", "b200disort_set_stream", "b200disort_set_warp_solve_max", "b200disort_set_layer_split", "b200disort_fp64_peak", "b200disort_destroy",
            "b200disort_strerror", "b200disort_version")
 BAND_EXPORTS = ("b200_band_create", "b200_band_nprop", "b200_band_optical_props", "b200_band_forward", "b200_band_forward_host", "b200_band_check",
                 "b200_band_allreduce", "b200_band_solver", "b200_band_destroy", "b200disort_allreduce_band",
@@ -138,6 +138,8 @@ def lib():
     L.b200disort_allreduce_band.argtypes = [vp, vp, vp]
     L.b200disort_solve_band.restype = C.c_int
     L.b200disort_solve_band.argtypes = [vp, vp, C.c_int, C.POINTER(BC), vp, vp, vp, vp]
+    L.b200disort_set_layer_split.restype = C.c_int
+    L.b200disort_set_layer_split.argtypes = [vp, C.c_int]
     L.b200disort_set_warp_solve_max.restype = C.c_int
     L.b200disort_set_warp_solve_max.argtypes = [vp, C.c_long]
     L.b200disort_set_stream.restype = C.c_int

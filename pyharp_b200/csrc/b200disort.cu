@@ -306,6 +306,9 @@ static int ring_end(b200disort_handle* h, cudaStream_t stream) {
   return B200DISORT_OK;
 }
 
+// which stream counts take the layer-split form by default (measured, profiles/r02/sweeps.md e36)
+static int split_default(int nn) { return nn >= 6 ? 1 : 0; }
+
 // Launch the flux kernel for p.nlocal solves on `stream` with the given back-sweep workspace.
 // timed = record the launch in the handle's event ring (handle stream only).
 int b200::launch_flux(b200disort_handle* h, SolveParams& p, cudaStream_t stream, double** ws, size_t* ws_bytes,
@@ -340,6 +343,34 @@ int b200::launch_flux(b200disort_handle* h, SolveParams& p, cudaStream_t stream,
         if (rc != B200DISORT_OK) return rc;
       }
       h->stats.kernel_launches += 1;
+      h->stats.workspace_bytes = *ws_bytes;
+      return B200DISORT_OK;
+    }
+  }
+  // nstr >= 12: the layer-split form (flux_inst.cu) -- layer phase as one thread per (solve, layer), adding recursion as
+  // one thread per solve, chunk by chunk through a scratch buffer.  B200DISORT_SPLIT / the handle's layer_split: 0 = the
+  // fused kernel, 1 = the split form, -1 = default (per stream count, see split_default).  B200DISORT_SPLIT_CHUNK =
+  // solves per chunk (default: two resident waves of the adding kernel).
+  if (inst->launch_split) {
+    static const int env_split = std::getenv("B200DISORT_SPLIT") ? std::atoi(std::getenv("B200DISORT_SPLIT")) : -1;
+    static const long env_chunk = std::getenv("B200DISORT_SPLIT_CHUNK") ? std::atol(std::getenv("B200DISORT_SPLIT_CHUNK")) : 0;
+    const int mode = h->layer_split >= 0 ? h->layer_split : env_split >= 0 ? env_split : split_default(inst->nn);
+    if (mode != 0) {
+      long chunk = env_chunk > 0 ? env_chunk : (long)h->sm_count * 256 * 2;
+      chunk = std::min<long>(chunk, p.nlocal);
+      const size_t need = inst->split_scratch(p.nlyr, chunk);
+      int rc = ensure_dev(ws, ws_bytes, need);
+      if (rc != B200DISORT_OK) return rc;
+      if (timed) {
+        rc = ring_begin(h, stream);
+        if (rc != B200DISORT_OK) return rc;
+      }
+      CU_TRY(inst->launch_split(p, chunk, h->sm_count, stream, *ws));
+      if (timed) {
+        rc = ring_end(h, stream);
+        if (rc != B200DISORT_OK) return rc;
+      }
+      h->stats.kernel_launches += 3 * (int)((p.nlocal + chunk - 1) / chunk);
       h->stats.workspace_bytes = *ws_bytes;
       return B200DISORT_OK;
     }
@@ -526,6 +557,12 @@ extern "C" int b200disort_set_stream(b200disort_handle* h, void* stream) {
   CU_TRY(cudaStreamSynchronize(h->stream));
   h->stream = (cudaStream_t)stream;
   h->cfg.stream = stream;
+  return B200DISORT_OK;
+}
+
+extern "C" int b200disort_set_layer_split(b200disort_handle* h, int mode) {
+  if (!h) return B200DISORT_ERR_INVALID;
+  h->layer_split = mode;
   return B200DISORT_OK;
 }
 

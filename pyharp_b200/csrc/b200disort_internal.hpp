@@ -17,6 +17,7 @@ struct b200disort_handle {
   int sm_count = 0;
   int occ = 0;  // resident CTAs per SM of the flux kernel
   int occ_warp = 0;  // ... of its warp-per-solve form
+  int layer_split = -1;  // nstr >= 12: 1 = layer-split form, 0 = fused kernel, -1 = default (b200disort_set_layer_split)
   long warp_solve_max = -1;  // largest batch sent to the warp-per-solve form (-1: one wave of warps)
   std::vector<double> user_tau, user_mu, user_phi, wave_lower, wave_upper;
   // device-side constants

@@ -586,6 +586,30 @@ B200_HD void solve_flux_layerwise(const SolveParams& p, const QT& qt, long s, do
   solve_flux_layerwise_u<NN, NOMOM, BAND>(p, qt, s, opsbuf, recbuf);
 }
 
+// Layer-split form (flux_inst.cu, nstr >= 12): the phases of a solve as separate kernels -- unrolled or rolled bodies
+// as for solve_flux_one
+template <int NN, typename QT>
+B200_HD void solve_common_any(const SolveParams& p, const QT& qt, long s, SolveCommon<NN>& c, bool bc_planck) {
+  if constexpr (NN <= B200_UNROLL_MAX_NN) solve_common_u<NN>(p, qt, s, c, bc_planck);
+  else solve_common_r<NN>(p, qt, s, c, bc_planck);
+}
+template <int NN, bool NOMOM>
+B200_HD void layer_depths_any(const SolveParams& p, const double* pr, int lc, double& dtp, double& dabs) {
+  layer_depths_u<NN, NOMOM>(p, pr, lc, dtp, dabs);
+}
+template <int NN, bool NOMOM, typename QT>
+B200_HD int layer_ops_any(const SolveParams& p, const QT& qt, const SolveCommon<NN>& cm, const double* pr, int lc, double taup,
+                          double* ops, long ostr) {
+  if constexpr (NN <= B200_UNROLL_MAX_NN) return layer_ops_u<NN, NOMOM>(p, qt, cm, pr, lc, taup, ops, ostr);
+  else return layer_ops_r<NN, NOMOM>(p, qt, cm, pr, lc, taup, ops, ostr);
+}
+template <int NN, int BAND, typename QT>
+B200_HD void adding_sweep_any(const SolveParams& p, const QT& qt, const SolveCommon<NN>& cm, long s, const double* pr, int ncut,
+                              bool lyrcut, int st, const double* opsbuf, double* recbuf, long bstr, long blane) {
+  if constexpr (NN <= B200_UNROLL_MAX_NN) adding_sweep_u<NN, BAND>(p, qt, cm, s, pr, ncut, lyrcut, st, opsbuf, recbuf, bstr, blane);
+  else adding_sweep_r<NN, BAND>(p, qt, cm, s, pr, ncut, lyrcut, st, opsbuf, recbuf, bstr, blane);
+}
+
 // finishes a pending (carried) back sweep after a thread's last solve
 template <int NN, int BAND = 0, typename QT>
 B200_HD void drain_back_sweep(const SolveParams& p, BackPend<NN>& pend, const QT& qt, long tid, unsigned& ring_pos) {

@@ -11,7 +11,16 @@
 #ifndef B200_SMEM_STACK
 #define B200_SMEM_STACK 0
 #endif
+#include <cstdlib>
+
 #include "flux_inst.cuh"
+// team form of the adding phase of the layer-split solve (four lanes per solve): nstr = 16
+#ifndef B200_HAVE_TEAM
+#define B200_HAVE_TEAM (B200_NN == 8)
+#endif
+#if B200_HAVE_TEAM
+#include "adding_team.cuh"
+#endif
 
 #ifndef B200_NN
 #error "compile with -DB200_NN=<nstr/2>"
@@ -168,6 +177,171 @@ cudaError_t launch_warp(const SolveParams& p, unsigned grid, int block, cudaStre
 }
 #endif
 
+// ---------------------------------------------------------------------------
+// Layer-split form (nstr >= 12).  At these stream counts the per-solve state of the fused kernel (~400 doubles at
+// nstr = 16) does not fit the register file: every thread carries a 3.5 KB spill frame, the frames of all resident
+// threads (~130 MB) overflow the L2 and the spills travel to HBM and back (ncu: 323 KB of local-memory traffic per
+// solve, long_scoreboard 3.6 stalls per issue, FP64 pipe 27 % busy).  The layers of a column are independent up to
+// the adding recursion, so the solve is cut where its live state is smallest:
+//   split_prefix_kernel   thread per solve: delta-M scaled optical depth at every layer top, absorption cut-off level
+//   split_layer_kernel    thread per (solve, layer): eigenproblem, particular solutions, R / T, layer sources
+//                         (disort_layer_ops.inc) -> hand-over record [warp block][layer][element][lane], 90 doubles at
+//                         nstr = 16; no stack operator, no adding-step matrices among its live values
+//   split_adding_kernel   thread per solve: adding recursion, bottom boundary, back sweep (disort_adding_step.inc);
+//                         none of the eigen-work among its live values
+// Both phases execute the statements of the fused kernel (the fragments are shared), so results agree with it to
+// rounding (the optical depth at a layer top comes from the same running sum).  The hand-over costs 2 x 720 B of HBM
+// traffic per layer and solve -- less than the spill traffic it removes -- and the layer phase has nlyr times the
+// parallelism of the batch, so small batches fill the GPU as well.
+// ---------------------------------------------------------------------------
+#if B200_NN >= 6
+#define B200_HAVE_SPLIT 1
+#else
+#define B200_HAVE_SPLIT 0
+#endif
+#if B200_HAVE_SPLIT
+#ifndef B200_SPLIT_MINB_A
+#define B200_SPLIT_MINB_A 1
+#endif
+#ifndef B200_SPLIT_MINB_B
+#define B200_SPLIT_MINB_B 1
+#endif
+constexpr int kSplitNoStatus = 0x7fffffff;
+
+__global__ void __launch_bounds__(128) split_prefix_kernel(SolveParams p, long c0, long cn, long cs, double* taup, int* cutv,
+                                                           int* stl) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cn) return;
+  const long s = c0 + i;
+  const int nlyr = p.nlyr;
+  const bool planck = (p.flags & F_PLANCK) != 0;
+  const double* pr = p.prop + s * nlyr * p.nprop;
+  double tp = 0.0, ab = 0.0;
+  int ncut = nlyr;
+  bool cut = false;
+  for (int lc = 0; lc < nlyr; ++lc) {
+    // c_disort_set: the medium is cut at the first layer above which the absorption optical depth reaches 10
+    if (!cut && !planck && nlyr > 1 && ab >= 10.0) { ncut = lc; cut = true; }
+    taup[(long)lc * cs + i] = tp;
+    double dtp, dabs;
+    layer_depths_any<B200_NN, false>(p, pr, lc, dtp, dabs);
+    tp += dtp;
+    ab += dabs;
+  }
+  const bool lyrcut = cut || (!planck && nlyr > 1 && ab >= 10.0);
+  cutv[i] = ncut | (lyrcut ? 0x10000 : 0);
+  stl[i] = kSplitNoStatus;
+}
+
+// (gw = solves per group of the hand-over buffer: kWsLanes for the thread form of the adding phase, kGrp for the team form)
+__global__ void __launch_bounds__(128, B200_SPLIT_MINB_A) split_layer_kernel(SolveParams p, long c0, long cn, long cs,
+                                                                              const double* taup, const int* cutv, double* ops,
+                                                                              int* stl, int gw) {
+  constexpr int NN = B200_NN, NOPS = kOpsDoubles<NN>;
+  const int nlyr = p.nlyr;
+  const long items = cn * nlyr, nthreads = (long)gridDim.x * blockDim.x;
+  for (long base = (long)blockIdx.x * blockDim.x; base < items; base += nthreads) {
+    B200_BLOCK_SYNC();  // the CTA's warps start every item together (instruction-cache sharing, as in the fused kernel)
+    const long t = base + threadIdx.x;
+    const bool in = t < items;
+    const long tt = in ? t : items - 1;  // threads beyond the end shadow the last item (the Jacobi sweeps vote per warp)
+    const int lc = (int)(tt / cn);
+    const long i = tt - (long)lc * cn;
+    const bool active = in && lc < (cutv[i] & 0xffff);  // layers below the cut-off are not examined
+    if (!__any_sync(0xffffffffu, active)) continue;
+    const long s = c0 + i;
+    SolveCommon<NN> cm;
+    solve_common_any<NN>(p, c_qt, s, cm, false);
+    const double* pr = p.prop + s * nlyr * p.nprop;
+    double* o = ops + (i / gw) * ((long)nlyr * NOPS * gw) + (long)lc * NOPS * gw + (i % gw);
+    const int st = layer_ops_any<NN, false>(p, c_qt, cm, pr, lc, taup[(long)lc * cs + i], o, gw);
+    if (active && st != ST_OK) atomicMin(stl + i, st);  // (bad input < eigen failure < singular: status_merge's order)
+  }
+}
+
+template <int BAND>
+__global__ void __launch_bounds__(128, B200_SPLIT_MINB_B) split_adding_kernel(SolveParams p, long c0, long cn, const int* cutv,
+                                                                               const int* stl, const double* ops, double* rec) {
+  constexpr int NN = B200_NN, NOPS = kOpsDoubles<NN>;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cn) return;
+  const long s = c0 + i;
+  const int nlyr = p.nlyr;
+  SolveCommon<NN> cm;
+  solve_common_any<NN>(p, c_qt, s, cm, true);
+  const double* pr = p.prop + s * nlyr * p.nprop;
+  const int cv = cutv[i], sl = stl[i];
+  const int st = status_merge_u(cm.st, sl == kSplitNoStatus ? (int)ST_OK : sl);
+  const long blk = i / kWsLanes, lane = i % kWsLanes;
+  adding_sweep_any<NN, BAND>(p, c_qt, cm, s, pr, cv & 0xffff, (cv >> 16) != 0, st, ops + blk * ((long)nlyr * NOPS * kWsLanes) + lane,
+                             rec + blk * ((long)nlyr * kNsave * kWsLanes) + lane, kWsLanes, lane);
+}
+
+#if B200_HAVE_TEAM
+template <int BAND>
+__global__ void __launch_bounds__(128, 2) team_adding_kernel(SolveParams p, long c0, long cn, const int* cutv, const int* stl,
+                                                             const double* ops, double* rec) {
+  extern __shared__ __align__(128) double b200_smem[];
+  team_adding_sweep<B200_NN, BAND>(p, c_qt, c0, cn, cutv, stl, ops, rec, b200_smem);
+}
+#endif
+
+long split_round(long chunk) { return (chunk + kWsLanes - 1) / kWsLanes * kWsLanes; }
+
+size_t split_scratch(int nlyr, long chunk) {
+  const long cs = split_round(chunk);
+  return (size_t)cs * nlyr * (kOpsDoubles<B200_NN> + kNsave + 1) * sizeof(double) + (size_t)cs * 2 * sizeof(int);
+}
+
+cudaError_t launch_split(const SolveParams& p, long chunk, int sm_count, cudaStream_t stream, void* scratch) {
+  const long cs = split_round(chunk);
+  const int nlyr = p.nlyr;
+  double* taup = static_cast<double*>(scratch);
+  double* ops = taup + (size_t)cs * nlyr;
+  double* rec = ops + (size_t)cs * nlyr * kOpsDoubles<B200_NN>;
+  int* cutv = reinterpret_cast<int*>(rec + (size_t)cs * nlyr * kNsave);
+  int* stl = cutv + cs;
+  static int occ_a = 0;
+  if (occ_a == 0) {
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, split_layer_kernel, 128, 0);
+    if (e != cudaSuccess) return e;
+    if (occ_a < 1) occ_a = 1;
+  }
+  const bool band = p.bflx_t != nullptr;
+  // adding phase: team form (four lanes per solve) where it is instantiated; B200DISORT_TEAM=0 selects the thread form
+  static const bool team = B200_HAVE_TEAM && !(std::getenv("B200DISORT_TEAM") && std::atoi(std::getenv("B200DISORT_TEAM")) == 0);
+#if B200_HAVE_TEAM
+  constexpr size_t kTeamSmem = (size_t)4 * TeamLayout<B200_NN>::kWarpDoubles * sizeof(double);
+  static bool attr_set = false;
+  if (team && !attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(team_adding_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTeamSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(team_adding_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTeamSmem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+#endif
+  const int gw = team ? 32 / 4 : kWsLanes;
+  for (long c0 = 0; c0 < p.nlocal; c0 += cs) {
+    const long cn = (p.nlocal - c0 < cs) ? p.nlocal - c0 : cs;
+    const unsigned gs = (unsigned)((cn + 127) / 128);
+    split_prefix_kernel<<<gs, 128, 0, stream>>>(p, c0, cn, cs, taup, cutv, stl);
+    const long ga = (cn * nlyr + 127) / 128, cap = (long)sm_count * occ_a;
+    split_layer_kernel<<<(unsigned)(ga < cap ? ga : cap), 128, 0, stream>>>(p, c0, cn, cs, taup, cutv, ops, stl, gw);
+#if B200_HAVE_TEAM
+    if (team) {
+      const unsigned gt = (unsigned)((cn + 31) / 32);  // 4 warps x 8 solves per CTA
+      if (band) team_adding_kernel<1><<<gt, 128, kTeamSmem, stream>>>(p, c0, cn, cutv, stl, ops, rec);
+      else team_adding_kernel<0><<<gt, 128, kTeamSmem, stream>>>(p, c0, cn, cutv, stl, ops, rec);
+      continue;
+    }
+#endif
+    if (band) split_adding_kernel<1><<<gs, 128, 0, stream>>>(p, c0, cn, cutv, stl, ops, rec);
+    else split_adding_kernel<0><<<gs, 128, 0, stream>>>(p, c0, cn, cutv, stl, ops, rec);
+  }
+  return cudaGetLastError();
+}
+#endif
+
 cudaError_t upload_tables(const QuadTables* qt) { return cudaMemcpyToSymbol(c_qt, qt, sizeof(QuadTables)); }
 
 // dynamic shared memory per CTA: the parked stack state (Ra packed symmetric + da) of every thread
@@ -237,10 +411,13 @@ cudaError_t launch(const SolveParams& p, unsigned grid, int block, cudaStream_t 
 
 #if B200_HAVE_WARP
 const FluxInst kInst = {B200_NN, B200_NN * B200_NN + 2 * B200_NN + 1, B200_MAX_THREADS, kCarryBack<B200_NN> ? 2 : 1, upload_tables, occupancy, launch,
-                        warp_scratch, warp_occupancy, launch_warp};
+                        warp_scratch, warp_occupancy, launch_warp, nullptr, nullptr};
+#elif B200_HAVE_SPLIT
+const FluxInst kInst = {B200_NN, B200_NN * B200_NN + 2 * B200_NN + 1, B200_MAX_THREADS, kCarryBack<B200_NN> ? 2 : 1, upload_tables, occupancy, launch,
+                        nullptr, nullptr, nullptr, split_scratch, launch_split};
 #else
 const FluxInst kInst = {B200_NN, B200_NN * B200_NN + 2 * B200_NN + 1, B200_MAX_THREADS, kCarryBack<B200_NN> ? 2 : 1, upload_tables, occupancy, launch,
-                        nullptr, nullptr, nullptr};
+                        nullptr, nullptr, nullptr, nullptr, nullptr};
 #endif
 
 }  // namespace

@@ -21,6 +21,11 @@ struct FluxInst {
   long (*warp_scratch)(int nlyr);
   cudaError_t (*warp_occupancy)(int block, int* blocks_per_sm);
   cudaError_t (*launch_warp)(const SolveParams&, unsigned grid, int block, cudaStream_t, double* scratch);
+  // layer-split form (null where it is not instantiated; nstr >= 12): the layer phase (eigenproblem ... R / T, sources)
+  // as one thread per (solve, layer), the adding recursion + back sweep as one thread per solve, chunk by chunk through a
+  // scratch buffer of split_scratch(nlyr, chunk) bytes
+  size_t (*split_scratch)(int nlyr, long chunk);
+  cudaError_t (*launch_split)(const SolveParams&, long chunk, int sm_count, cudaStream_t, void* scratch);
 };
 
 #define B200_DECL_INST(NN) const FluxInst* flux_inst_##NN();

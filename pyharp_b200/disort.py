@@ -213,6 +213,13 @@ class Disort:
             raise RuntimeError(_cabi.strerror(rc))
         return self
 
+    def set_layer_split(self, mode):
+        """nstr >= 12: 1 = layer-split form of the flux solve, 0 = the fused kernel, -1 = default for the stream count."""
+        rc = self._lib.b200disort_set_layer_split(self._h, int(mode))
+        if rc != _cabi.OK:
+            raise RuntimeError(_cabi.strerror(rc))
+        return self
+
     def ds(self, n=0, j=0):
         return self.options.ds()
 

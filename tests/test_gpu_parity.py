@@ -24,6 +24,22 @@ def _relerr(a, ref):
     return float(np.max(np.abs(a - ref) / scale))
 
 
+FORMS = ["thread_per_solve", "warp_per_solve", "layer_split"]
+
+
+def _skip_form(form, nstr):
+    if form == "warp_per_solve" and nstr > 8:
+        pytest.skip("the warp-per-solve form is instantiated for nstr <= 8")
+    if form == "layer_split" and nstr < 12:
+        pytest.skip("the layer-split form is instantiated for nstr >= 12")
+
+
+def _with_form(ds, form):
+    """thread_per_solve = the fused kernel; warp_per_solve (nstr <= 8) / layer_split (nstr >= 12) forced on."""
+    ds.set_warp_solve_max(1 << 30 if form == "warp_per_solve" else 0)
+    return ds.set_layer_split(1 if form == "layer_split" else 0)
+
+
 CASES = [
     ("test1a", dict()),
     ("amars_sw", dict(nwave=64, ncol=3, nlyr=40)),
@@ -37,15 +53,14 @@ CASES = [
 
 @pytest.mark.parametrize("name,kw", CASES, ids=[f"{n}-{i}" for i, (n, _) in enumerate(CASES)])
 @pytest.mark.parametrize("where", ["host", "device"])
-@pytest.mark.parametrize("form", ["thread_per_solve", "warp_per_solve"])
+@pytest.mark.parametrize("form", FORMS)
 def test_flux_parity(cuda_device, name, kw, where, form):
-    """Both forms of the flux kernel: small batches default to the warp-per-solve form (nstr <= 8), which is forced off /
-    on here so that each case runs on each form that exists for its stream count."""
+    """Every form of the flux kernel: small batches default to the warp-per-solve form (nstr <= 8) and nstr >= 12 to the
+    layer-split form; each is forced off / on here so that each case runs on each form that exists for its stream count."""
     wl = W.make(name, **kw)
-    if form == "warp_per_solve" and wl.nstr > 8:
-        pytest.skip("the warp-per-solve form is instantiated for nstr <= 8")
+    _skip_form(form, wl.nstr)
     ref = _oracle(wl)
-    ds = Disort(wl.options()).set_warp_solve_max(0 if form == "thread_per_solve" else 1 << 30)
+    ds = _with_form(Disort(wl.options()), form)
     dev = "cpu" if where == "host" else cuda_device
     t = lambda a: None if a is None else torch.from_numpy(a).to(dev)
     flx = ds.forward(t(wl.prop), {k: t(v) for k, v in wl.bc.items()}, t(wl.temf))
@@ -95,14 +110,13 @@ import golden_lib as G  # noqa: E402
 
 
 @pytest.mark.parametrize("name", G.NAMES)
-@pytest.mark.parametrize("form", ["thread_per_solve", "warp_per_solve"])
+@pytest.mark.parametrize("form", FORMS)
 def test_golden_fixtures(cuda_device, name, form):
     """Committed fixtures: extended-precision oracle, independent numpy solve, and (amars_sw_real) the real
-    inputs of the reference's examples/amars_sw.cpp; on both forms of the flux kernel."""
+    inputs of the reference's examples/amars_sw.cpp; on every form of the flux kernel."""
     wl, ld, ind, valid = G.load(name)
-    if form == "warp_per_solve" and wl.nstr > 8:
-        pytest.skip("the warp-per-solve form is instantiated for nstr <= 8")
-    ds = Disort(wl.options()).set_warp_solve_max(0 if form == "thread_per_solve" else 1 << 30)
+    _skip_form(form, wl.nstr)
+    ds = _with_form(Disort(wl.options()), form)
     t = lambda a: None if a is None else torch.from_numpy(a).to(cuda_device)
     flx = ds.forward(t(wl.prop), {k: t(v) for k, v in wl.bc.items()}, t(wl.temf)).cpu().numpy()
     G.check(flx, ld, RTOL)  # fluxes and per-layer net-flux divergence
@@ -136,8 +150,53 @@ def test_every_stream_count(cuda_device, nstr, thermal):
     wl = W.Workload("streams", nstr, tokens, prop, bc, temf, kw.get("wave_lower"), kw.get("wave_upper"))
     ref = _oracle(wl)
     t = lambda a: None if a is None else torch.from_numpy(a).to(cuda_device)
-    for limit in ((0, 1 << 30) if nstr <= 8 else (0,)):  # thread-per-solve, then (where it exists) warp-per-solve
-        ds = Disort(wl.options()).set_warp_solve_max(limit)
+    # the fused kernel, then (where they exist) the warp-per-solve / layer-split forms
+    for form in ("thread_per_solve", "warp_per_solve" if nstr <= 8 else "layer_split"):
+        if form == "layer_split" and nstr < 12:
+            continue
+        ds = _with_form(Disort(wl.options()), form)
         flx = ds.forward(t(prop), {k: t(v) for k, v in bc.items()}, t(temf)).cpu().numpy()
         assert _relerr(flx, ref) < RTOL
         assert G.diverr(flx, ref) < RTOL
+
+
+@pytest.mark.parametrize("nstr", [12, 16])
+def test_layer_split_matches_fused_kernel(cuda_device, nstr):
+    """nstr >= 12: the layer-split form against the fused kernel on a batch with absorption cut-offs at different
+    levels, zero-thickness layers and a rejected input: same status words,
+    fluxes equal to rounding (both execute the same statements; only the launch structure differs)."""
+    rng = np.random.default_rng(7 + nstr)
+    nw, nc, nl = 5, 77, 23
+    prop = np.zeros((nw, nc, nl, 2 + nstr))
+    prop[..., 0] = 10.0 ** rng.uniform(-3, 0.9, (nw, nc, nl))
+    prop[..., 1] = rng.uniform(0.0, 0.999, (nw, nc, nl))
+    prop[:, ::7, :, 1] *= 0.05                     # strongly absorbing columns: cut off part of the way down
+    prop[:, 3::11, 5:8, 0] = 0.0                   # zero-thickness layers
+    g = rng.uniform(0.0, 0.85, (nw, nc, nl))
+    for k in range(nstr):
+        prop[..., 2 + k] = g ** (k + 1)
+    prop[2, 40, 9, 1] = 1.25                       # c_check_inputs: ssalb > 1
+    bc = {"fbeam": rng.uniform(1, 4, (nw, nc)), "umu0": rng.uniform(0.15, 0.95, (nw, nc)), "albedo": rng.uniform(0, 1, (nw, nc))}
+    x, _ = np.polynomial.legendre.leggauss(nstr // 2)
+    for q in 0.5 * (x + 1):
+        bc["umu0"] = np.where(np.abs(bc["umu0"] - q) / bc["umu0"] < 1e-3, bc["umu0"] * 1.01, bc["umu0"])
+    wl = W.Workload("split", nstr, "lamber,quiet,onlyfl", prop, bc, None, None, None)
+    t = lambda a: torch.from_numpy(a).to(cuda_device)
+    status = []
+    for split in (0, 1):
+        ds = Disort(wl.options()).set_layer_split(split)
+        with pytest.raises(RuntimeError, match="solves failed"):
+            ds.forward(t(prop), {k: t(v) for k, v in bc.items()})
+        status.append(ds.status().cpu().numpy())
+    assert np.array_equal(status[0], status[1]) and status[0][2, 40] == 1 and status[0].sum() == 1
+    # fluxes of the accepted solves: drop the rejected input and compare the two forms
+    prop[2, 40, 9, 1] = 0.5
+    res = []
+    for split in (0, 1):
+        ds = Disort(wl.options()).set_layer_split(split)
+        res.append(ds.forward(t(prop), {k: t(v) for k, v in bc.items()}).cpu().numpy())
+        assert int(ds.status().abs().sum()) == 0
+    scale = np.max(np.abs(res[0]), axis=(2, 3), keepdims=True)
+    assert float(np.max(np.abs(res[0] - res[1]) / scale)) < 1e-12
+    assert (res[0][:, ::7, 0, 1] == 0).any()       # some columns are cut off before the surface
+    assert _relerr(res[1], _oracle(wl)) < RTOL

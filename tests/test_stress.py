@@ -82,11 +82,12 @@ def test_gpu_stress(cuda_device, nstr):
         op.ds().nlyr, op.ds().nstr, op.ds().nmom = nl, nstr, nstr
         if th:
             op.wave_lower(list(c["wave_lower"])).wave_upper(list(c["wave_upper"]))
-        ds = Disort(op)
         t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device)
-        flx = ds.forward(t(c["prop"]), {k: t(v) for k, v in c["bc"].items()}, t(c["temf"])).cpu().numpy()
-        assert int(ds.status().abs().sum()) == 0
-        _bar(c, flx)
+        for split in ((0, 1) if nstr >= 12 else (0,)):  # the fused kernel and (nstr >= 12) the layer-split form
+            ds = Disort(op).set_layer_split(split)
+            flx = ds.forward(t(c["prop"]), {k: t(v) for k, v in c["bc"].items()}, t(c["temf"])).cpu().numpy()
+            assert int(ds.status().abs().sum()) == 0
+            _bar(c, flx)
 
 
 @pytest.mark.gpu
