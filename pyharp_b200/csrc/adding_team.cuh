@@ -11,7 +11,7 @@
 //     contiguous in the [group of 8 solves][layer][element][solve] layout the layer kernel writes) is staged in shared
 //     memory by ONE bulk copy (cp.async.bulk + mbarrier, two buffers: the copy of layer lc + 2 is issued as soon as
 //     layer lc has been read), so no lane ever waits on a global load in the forward sweep;
-//   * operands every lane of the team needs (the stack operator, the pivot row of the elimination, M1 | v1, Ra M1) are
+//   * operands every lane of the team needs (the stack operator, the pivot rows of the elimination, M1 | v1) are
 //     exchanged through per-team slabs in shared memory and read back with broadcast loads (row stride nn + 2 doubles
 //     and a team stride of an odd number of 16-byte chunks keep the row stores of the 8 lanes of a quarter warp and
 //     the broadcast reads of the 8 teams of a warp on distinct banks);
@@ -39,9 +39,9 @@ struct TeamLayout {
   static constexpr int RS = NN + 2;                       // slab row stride (doubles): rows start on 16-byte boundaries
   static constexpr int kPivDoubles = 2 * NN + 2;          // pivot row: A part (NN) | right-hand sides (NN + 1) | pad
   static constexpr int kRaOff = 0;                        // Ra | da            NN rows x RS
-  static constexpr int kXOff = NN * RS;                   // M1 | v1, then Ra M1 NN rows x RS
-  static constexpr int kPivOff = 2 * NN * RS;             // two pivot rows
-  static constexpr int kTeamRaw = 2 * NN * RS + 2 * kPivDoubles;
+  static constexpr int kXOff = NN * RS;                   // M1 | v1            NN rows x RS
+  static constexpr int kPivOff = 2 * NN * RS;             // two buffers of (R == 2: two) pivot rows
+  static constexpr int kTeamRaw = 2 * NN * RS + (R == 2 ? 4 : 2) * kPivDoubles;
   // team stride: an odd number of 16-byte chunks (mod 8 chunks = 128 bytes)
   static constexpr int kTeamDoubles = ((kTeamRaw / 2) % 2 == 1) ? kTeamRaw : kTeamRaw + 2;
   static constexpr int kStageDoubles = NOPS * kGrp;       // one layer of the warp's group
@@ -84,7 +84,7 @@ __device__ __forceinline__ void team_adding_sweep(const SolveParams& p, const QT
   __syncwarp();
 
   SolveCommon<NN> cm;
-  solve_common_any<NN>(p, qt, s, cm, true);
+  solve_common_any<NN>(p, qt, s, cm, true, false);
   const double* pr = p.prop + s * nlyr * nprop;
   const int cv = valid ? cutv[i] : cutv[cn - 1], sl = valid ? stl[i] : stl[cn - 1];
   const int ncut = cv & 0xffff;
@@ -149,16 +149,18 @@ __device__ __forceinline__ void team_adding_sweep(const SolveParams& p, const QT
     if (lane == 0 && lc + 2 < ncw)
       b200_tma_load(stage0 + buf * L::kStageDoubles, ops_g + (long)(lc + 2) * NOPS * kGrp, L::kStageBytes, bars + buf);
 
-    // ---- A = I - R Ra, right-hand sides [T | R da + s+]
-    double A[R][NN], B[R][NN + 1];
+    // ---- A = I - R Ra, right-hand sides [T | R da + s+]; and TR = T Ra, td = T da for the stack update below
+    double A[R][NN], B[R][NN + 1], TR[R][NN], td[R];
 #pragma unroll
     for (int a = 0; a < R; ++a) {
 #pragma unroll
       for (int c = 0; c < NN; ++c) {
         A[a][c] = (R * r + a == c) ? 1.0 : 0.0;
         B[a][c] = tl[a][c];
+        TR[a][c] = 0.0;
       }
       B[a][NN] = spv[a];
+      td[a] = 0.0;
     }
 #pragma unroll
     for (int k = 0; k < NN; ++k) {
@@ -172,12 +174,72 @@ __device__ __forceinline__ void team_adding_sweep(const SolveParams& p, const QT
 #pragma unroll
       for (int a = 0; a < R; ++a) {
 #pragma unroll
-        for (int c = 0; c < NN; ++c) A[a][c] = fma(-rl[a][k], row[c], A[a][c]);
+        for (int c = 0; c < NN; ++c) {
+          A[a][c] = fma(-rl[a][k], row[c], A[a][c]);
+          TR[a][c] = fma(tl[a][k], row[c], TR[a][c]);
+        }
         B[a][NN] = fma(rl[a][k], row[NN], B[a][NN]);
+        td[a] = fma(tl[a][k], row[NN], td[a]);
       }
     }
 
     // ---- Gauss-Jordan elimination in the natural order: [A | B] -> [I | A^-1 B]
+    if constexpr (R == 2) {
+      // by 2 x 2 pivot blocks: both rows of a block belong to ONE lane, which applies the inverse of its diagonal block
+      // (one reciprocal of the determinant: four dependent reciprocal chains per layer instead of eight, and half the
+      // publish -> synchronise -> read round trips) and publishes both rows
+#pragma unroll
+      for (int q = 0; q < kTeam; ++q) {
+        constexpr int PD = L::kPivDoubles;
+        double* pv = Pv + (q & 1) * 2 * PD;
+        const int k0 = 2 * q;
+        if (r == q) {
+          const double a00 = A[0][k0], a01 = A[0][k0 + 1], a10 = A[1][k0], a11 = A[1][k0 + 1];
+          const double det = fma(a00, a11, -a01 * a10);
+          piv.add(a00);
+          piv.add(det);
+          const double rd = B200_RCP(det);
+          const double i00 = a11 * rd, i01 = -a01 * rd, i10 = -a10 * rd, i11 = a00 * rd;
+#pragma unroll
+          for (int c = 0; c < NN; ++c)
+            if (c > k0 + 1) {
+              const double x = A[0][c], y = A[1][c];
+              A[0][c] = fma(i00, x, i01 * y);
+              A[1][c] = fma(i10, x, i11 * y);
+            }
+#pragma unroll
+          for (int c = 0; c <= NN; ++c) {
+            const double x = B[0][c], y = B[1][c];
+            B[0][c] = fma(i00, x, i01 * y);
+            B[1][c] = fma(i10, x, i11 * y);
+          }
+#pragma unroll
+          for (int c = 0; c < 2 * NN + 2; c += 2)
+            if (c + 1 > k0 + 1) {
+              b200_st2(pv + c, c < NN ? A[0][c] : B[0][c - NN], c + 1 < NN ? A[0][c + 1] : (c + 1 - NN <= NN ? B[0][c + 1 - NN] : 0.0));
+              b200_st2(pv + PD + c, c < NN ? A[1][c] : B[1][c - NN], c + 1 < NN ? A[1][c + 1] : (c + 1 - NN <= NN ? B[1][c + 1 - NN] : 0.0));
+            }
+        }
+        __syncwarp();
+        double p0[2 * NN + 2], p1[2 * NN + 2];
+#pragma unroll
+        for (int c = 0; c < 2 * NN + 2; c += 2)
+          if (c + 1 > k0 + 1) {
+            const double2 u = b200_ld2(pv + c), v = b200_ld2(pv + PD + c);
+            p0[c] = u.x; p0[c + 1] = u.y;
+            p1[c] = v.x; p1[c + 1] = v.y;
+          }
+#pragma unroll
+        for (int a = 0; a < R; ++a) {
+          const double f0 = (r == q) ? 0.0 : A[a][k0], f1 = (r == q) ? 0.0 : A[a][k0 + 1];
+#pragma unroll
+          for (int c = 0; c < NN; ++c)
+            if (c > k0 + 1) A[a][c] = fma(-f1, p1[c], fma(-f0, p0[c], A[a][c]));
+#pragma unroll
+          for (int c = 0; c <= NN; ++c) B[a][c] = fma(-f1, p1[NN + c], fma(-f0, p0[NN + c], B[a][c]));
+        }
+      }
+    } else {
 #pragma unroll
     for (int k = 0; k < NN; ++k) {
       const int owner = k / R, slot = k % R;
@@ -218,6 +280,7 @@ __device__ __forceinline__ void team_adding_sweep(const SolveParams& p, const QT
         for (int c = 0; c <= NN; ++c) B[a][c] = fma(-f, prow[NN + c], B[a][c]);
       }
     }
+    }
     // B = [M1 | v1]
 
     // ---- this level's back-sweep record: M1, v1, c^T Ra, c^T da (c = 2 pi t)
@@ -245,7 +308,8 @@ __device__ __forceinline__ void team_adding_sweep(const SolveParams& p, const QT
       }
     }
 
-    // ---- RM = Ra [M1 | v1] (+ da in the last column: dv = da + Ra v1)
+    // ---- new stack: Ra' = R + T Ra M1 = R + TR M1,  da' = s- + T (da + Ra v1) = s- + T da + TR v1  (TR = T Ra and T da were
+    //      formed with the rows of Ra | da read for A above: one broadcast of [M1 | v1] instead of two exchanges)
 #pragma unroll
     for (int a = 0; a < R; ++a) {
 #pragma unroll
@@ -253,42 +317,12 @@ __device__ __forceinline__ void team_adding_sweep(const SolveParams& p, const QT
       Xs[(R * r + a) * RS + NN] = B[a][NN];
     }
     __syncwarp();
-    double RM[R][NN + 1];
-#pragma unroll
-    for (int a = 0; a < R; ++a) {
-#pragma unroll
-      for (int c = 0; c < NN; ++c) RM[a][c] = 0.0;
-      RM[a][NN] = dav[a];
-    }
-#pragma unroll
-    for (int k = 0; k < NN; ++k) {
-      double row[NN + 2];
-#pragma unroll
-      for (int c = 0; c < NN + 2; c += 2) {
-        const double2 v = b200_ld2(Xs + k * RS + c);
-        row[c] = v.x;
-        row[c + 1] = v.y;
-      }
-#pragma unroll
-      for (int a = 0; a < R; ++a)
-#pragma unroll
-        for (int c = 0; c <= NN; ++c) RM[a][c] = fma(ra[a][k], row[c], RM[a][c]);
-    }
-    __syncwarp();  // M1 | v1 has been read by every lane: the slab takes RM
-#pragma unroll
-    for (int a = 0; a < R; ++a) {
-#pragma unroll
-      for (int c = 0; c < NN; c += 2) b200_st2(Xs + (R * r + a) * RS + c, RM[a][c], RM[a][c + 1]);
-      Xs[(R * r + a) * RS + NN] = RM[a][NN];
-    }
-    __syncwarp();
-    // ---- new stack: Ra' = R + T RM, da' = s- + T dv
     double rn[R][NN], dn[R];
 #pragma unroll
     for (int a = 0; a < R; ++a) {
 #pragma unroll
       for (int c = 0; c < NN; ++c) rn[a][c] = rl[a][c];
-      dn[a] = smv[a];
+      dn[a] = smv[a] + td[a];
     }
 #pragma unroll
     for (int k = 0; k < NN; ++k) {
@@ -302,8 +336,8 @@ __device__ __forceinline__ void team_adding_sweep(const SolveParams& p, const QT
 #pragma unroll
       for (int a = 0; a < R; ++a) {
 #pragma unroll
-        for (int c = 0; c < NN; ++c) rn[a][c] = fma(tl[a][k], row[c], rn[a][c]);
-        dn[a] = fma(tl[a][k], row[NN], dn[a]);
+        for (int c = 0; c < NN; ++c) rn[a][c] = fma(TR[a][k], row[c], rn[a][c]);
+        dn[a] = fma(TR[a][k], row[NN], dn[a]);
       }
     }
     if (act) {  // (a team whose medium is cut off higher up keeps its stack)
@@ -402,8 +436,15 @@ __device__ __forceinline__ void team_adding_sweep(const SolveParams& p, const QT
   };
   double cur[NREC], nxt[NREC];
   if (ncut > 0) load_rec(cur, ncut - 1);
+  constexpr int kRecLines = (NSAVE * kGrp * 8 + 127) / 128;  // 128-byte lines of the warp's record of one level
   for (int lev = ncw - 1; lev >= 0; --lev) {  // (warp-uniform trip count: the all-gather below is a warp operation)
     const bool own = lev < ncut;
+    if (lev >= 4) {  // the record four levels up is pulled into the L2 behind this level's arithmetic
+      const char* pl = reinterpret_cast<const char*>(rec_g - tj + (long)(lev - 4) * NSAVE * kGrp);
+#pragma unroll
+      for (int l0 = 0; l0 < kRecLines; l0 += 32)
+        if (l0 + lane < kRecLines) asm volatile("prefetch.global.L2 [%0];" ::"l"(pl + (long)(l0 + lane) * 128));
+    }
     if (own && lev > 0) load_rec(nxt, lev - 1);
     double nu[R];
     double fup = 0.0, fdn = 0.0;

@@ -306,8 +306,9 @@ static int ring_end(b200disort_handle* h, cudaStream_t stream) {
   return B200DISORT_OK;
 }
 
-// which stream counts take the layer-split form by default (measured, profiles/r02/sweeps.md e36)
-static int split_default(int nn) { return nn >= 6 ? 1 : 0; }
+// which stream counts take the layer-split form by default (measured, profiles/r02/sweeps.md e36: nstr = 12 loses 14 %,
+// nstr = 16 / 24 / 32 gain 1.3-1.9x / 1.3x / 2x)
+static int split_default(int nn) { return nn >= 8 ? 1 : 0; }
 
 // Launch the flux kernel for p.nlocal solves on `stream` with the given back-sweep workspace.
 // timed = record the launch in the handle's event ring (handle stream only).

@@ -295,6 +295,12 @@ constexpr int kMaxSweeps = 16;
 #ifndef B200_PIPE_PM_MAX_NN
 #define B200_PIPE_PM_MAX_NN 4
 #endif
+// smallest nn at which Z = L Y is not formed (disort_layer_ops.inc, kNoZT).  Measured at nstr = 16 (profiles/r02/sweeps.md,
+// e37): 4 % SLOWER in the layer kernel although it executes 3 % fewer flops -- L and Y stay live through the particular
+// solutions and ptxas spills more (3.5 KB of spill stores per layer against 3.0 KB) -- so it is off
+#ifndef B200_NOZT_MIN_NN
+#define B200_NOZT_MIN_NN 99
+#endif
 #ifndef B200_BS_DEPTH
 #define B200_BS_DEPTH 3
 #endif
@@ -589,9 +595,9 @@ B200_HD void solve_flux_layerwise(const SolveParams& p, const QT& qt, long s, do
 // Layer-split form (flux_inst.cu, nstr >= 12): the phases of a solve as separate kernels -- unrolled or rolled bodies
 // as for solve_flux_one
 template <int NN, typename QT>
-B200_HD void solve_common_any(const SolveParams& p, const QT& qt, long s, SolveCommon<NN>& c, bool bc_planck) {
-  if constexpr (NN <= B200_UNROLL_MAX_NN) solve_common_u<NN>(p, qt, s, c, bc_planck);
-  else solve_common_r<NN>(p, qt, s, c, bc_planck);
+B200_HD void solve_common_any(const SolveParams& p, const QT& qt, long s, SolveCommon<NN>& c, bool bc_planck, bool legendre) {
+  if constexpr (NN <= B200_UNROLL_MAX_NN) solve_common_u<NN>(p, qt, s, c, bc_planck, legendre);
+  else solve_common_r<NN>(p, qt, s, c, bc_planck, legendre);
 }
 template <int NN, bool NOMOM>
 B200_HD void layer_depths_any(const SolveParams& p, const double* pr, int lc, double& dtp, double& dabs) {
@@ -599,9 +605,9 @@ B200_HD void layer_depths_any(const SolveParams& p, const double* pr, int lc, do
 }
 template <int NN, bool NOMOM, typename QT>
 B200_HD int layer_ops_any(const SolveParams& p, const QT& qt, const SolveCommon<NN>& cm, const double* pr, int lc, double taup,
-                          double* ops, long ostr) {
-  if constexpr (NN <= B200_UNROLL_MAX_NN) return layer_ops_u<NN, NOMOM>(p, qt, cm, pr, lc, taup, ops, ostr);
-  else return layer_ops_r<NN, NOMOM>(p, qt, cm, pr, lc, taup, ops, ostr);
+                          double* ops, long ostr, const double* y0p, long y0s) {
+  if constexpr (NN <= B200_UNROLL_MAX_NN) return layer_ops_u<NN, NOMOM>(p, qt, cm, pr, lc, taup, ops, ostr, y0p, y0s);
+  else return layer_ops_r<NN, NOMOM>(p, qt, cm, pr, lc, taup, ops, ostr, y0p, y0s);
 }
 template <int NN, int BAND, typename QT>
 B200_HD void adding_sweep_any(const SolveParams& p, const QT& qt, const SolveCommon<NN>& cm, long s, const double* pr, int ncut,

@@ -200,6 +200,10 @@ cudaError_t launch_warp(const SolveParams& p, unsigned grid, int block, cudaStre
 #define B200_HAVE_SPLIT 0
 #endif
 #if B200_HAVE_SPLIT
+// Legendre polynomials at the beam angle: 1 = read from the prefix pass's buffer where they are used, 0 = recomputed per item
+#ifndef B200_SPLIT_Y0BUF
+#define B200_SPLIT_Y0BUF 1
+#endif
 #ifndef B200_SPLIT_MINB_A
 #define B200_SPLIT_MINB_A 1
 #endif
@@ -208,12 +212,18 @@ cudaError_t launch_warp(const SolveParams& p, unsigned grid, int block, cudaStre
 #endif
 constexpr int kSplitNoStatus = 0x7fffffff;
 
-__global__ void __launch_bounds__(128) split_prefix_kernel(SolveParams p, long c0, long cn, long cs, double* taup, int* cutv,
-                                                           int* stl) {
+__global__ void __launch_bounds__(128) split_prefix_kernel(SolveParams p, long c0, long cn, long cs, double* taup, double* y0b,
+                                                           int* cutv, int* stl) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cn) return;
   const long s = c0 + i;
   const int nlyr = p.nlyr;
+  {  // Legendre polynomials at the beam angle (c_legendre_poly, m = 0): once per solve, not once per layer
+    SolveCommon<B200_NN> cm;
+    solve_common_any<B200_NN>(p, c_qt, s, cm, false, true);
+#pragma unroll
+    for (int l = 0; l < 2 * B200_NN; ++l) y0b[(long)l * cs + i] = cm.y0[l];
+  }
   const bool planck = (p.flags & F_PLANCK) != 0;
   const double* pr = p.prop + s * nlyr * p.nprop;
   double tp = 0.0, ab = 0.0;
@@ -235,27 +245,35 @@ __global__ void __launch_bounds__(128) split_prefix_kernel(SolveParams p, long c
 
 // (gw = solves per group of the hand-over buffer: kWsLanes for the thread form of the adding phase, kGrp for the team form)
 __global__ void __launch_bounds__(128, B200_SPLIT_MINB_A) split_layer_kernel(SolveParams p, long c0, long cn, long cs,
-                                                                              const double* taup, const int* cutv, double* ops,
-                                                                              int* stl, int gw) {
+                                                                              const double* taup, const double* y0b,
+                                                                              const int* cutv, double* ops, int* stl, int gw) {
   constexpr int NN = B200_NN, NOPS = kOpsDoubles<NN>;
   const int nlyr = p.nlyr;
   const long items = cn * nlyr, nthreads = (long)gridDim.x * blockDim.x;
-  for (long base = (long)blockIdx.x * blockDim.x; base < items; base += nthreads) {
+  // item t = (layer t / cn, solve t % cn): one division per thread, then both indices advance with the grid stride
+  long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  int lc = (int)(t / cn);
+  long i = t - (long)lc * cn;
+  const int dl = (int)(nthreads / cn);
+  const long di = nthreads - (long)dl * cn;
+  for (long base = (long)blockIdx.x * blockDim.x; base < items; base += nthreads, t += nthreads) {
     B200_BLOCK_SYNC();  // the CTA's warps start every item together (instruction-cache sharing, as in the fused kernel)
-    const long t = base + threadIdx.x;
     const bool in = t < items;
-    const long tt = in ? t : items - 1;  // threads beyond the end shadow the last item (the Jacobi sweeps vote per warp)
-    const int lc = (int)(tt / cn);
-    const long i = tt - (long)lc * cn;
-    const bool active = in && lc < (cutv[i] & 0xffff);  // layers below the cut-off are not examined
+    const int lcc = in ? lc : nlyr - 1;  // threads beyond the end shadow the last item (the Jacobi sweeps vote per warp)
+    const long ic = in ? i : cn - 1;
+    lc += dl;
+    i += di;
+    if (i >= cn) { i -= cn; ++lc; }
+    const bool active = in && lcc < (cutv[ic] & 0xffff);  // layers below the cut-off are not examined
     if (!__any_sync(0xffffffffu, active)) continue;
-    const long s = c0 + i;
+    const long s = c0 + ic;
     SolveCommon<NN> cm;
-    solve_common_any<NN>(p, c_qt, s, cm, false);
+    solve_common_any<NN>(p, c_qt, s, cm, false, !B200_SPLIT_Y0BUF);
     const double* pr = p.prop + s * nlyr * p.nprop;
-    double* o = ops + (i / gw) * ((long)nlyr * NOPS * gw) + (long)lc * NOPS * gw + (i % gw);
-    const int st = layer_ops_any<NN, false>(p, c_qt, cm, pr, lc, taup[(long)lc * cs + i], o, gw);
-    if (active && st != ST_OK) atomicMin(stl + i, st);  // (bad input < eigen failure < singular: status_merge's order)
+    double* o = ops + (ic / gw) * ((long)nlyr * NOPS * gw) + (long)lcc * NOPS * gw + (ic % gw);
+    const int st = layer_ops_any<NN, false>(p, c_qt, cm, pr, lcc, taup[(long)lcc * cs + ic], o, gw,
+                                            B200_SPLIT_Y0BUF ? y0b + ic : nullptr, B200_SPLIT_Y0BUF ? cs : 1);
+    if (active && st != ST_OK) atomicMin(stl + ic, st);  // (bad input < eigen failure < singular: status_merge's order)
   }
 }
 
@@ -268,7 +286,7 @@ __global__ void __launch_bounds__(128, B200_SPLIT_MINB_B) split_adding_kernel(So
   const long s = c0 + i;
   const int nlyr = p.nlyr;
   SolveCommon<NN> cm;
-  solve_common_any<NN>(p, c_qt, s, cm, true);
+  solve_common_any<NN>(p, c_qt, s, cm, true, false);
   const double* pr = p.prop + s * nlyr * p.nprop;
   const int cv = cutv[i], sl = stl[i];
   const int st = status_merge_u(cm.st, sl == kSplitNoStatus ? (int)ST_OK : sl);
@@ -290,14 +308,15 @@ long split_round(long chunk) { return (chunk + kWsLanes - 1) / kWsLanes * kWsLan
 
 size_t split_scratch(int nlyr, long chunk) {
   const long cs = split_round(chunk);
-  return (size_t)cs * nlyr * (kOpsDoubles<B200_NN> + kNsave + 1) * sizeof(double) + (size_t)cs * 2 * sizeof(int);
+  return (size_t)cs * (nlyr * (kOpsDoubles<B200_NN> + kNsave + 1) + 2 * B200_NN) * sizeof(double) + (size_t)cs * 2 * sizeof(int);
 }
 
 cudaError_t launch_split(const SolveParams& p, long chunk, int sm_count, cudaStream_t stream, void* scratch) {
   const long cs = split_round(chunk);
   const int nlyr = p.nlyr;
   double* taup = static_cast<double*>(scratch);
-  double* ops = taup + (size_t)cs * nlyr;
+  double* y0b = taup + (size_t)cs * nlyr;
+  double* ops = y0b + (size_t)cs * 2 * B200_NN;
   double* rec = ops + (size_t)cs * nlyr * kOpsDoubles<B200_NN>;
   int* cutv = reinterpret_cast<int*>(rec + (size_t)cs * nlyr * kNsave);
   int* stl = cutv + cs;
@@ -324,9 +343,9 @@ cudaError_t launch_split(const SolveParams& p, long chunk, int sm_count, cudaStr
   for (long c0 = 0; c0 < p.nlocal; c0 += cs) {
     const long cn = (p.nlocal - c0 < cs) ? p.nlocal - c0 : cs;
     const unsigned gs = (unsigned)((cn + 127) / 128);
-    split_prefix_kernel<<<gs, 128, 0, stream>>>(p, c0, cn, cs, taup, cutv, stl);
+    split_prefix_kernel<<<gs, 128, 0, stream>>>(p, c0, cn, cs, taup, y0b, cutv, stl);
     const long ga = (cn * nlyr + 127) / 128, cap = (long)sm_count * occ_a;
-    split_layer_kernel<<<(unsigned)(ga < cap ? ga : cap), 128, 0, stream>>>(p, c0, cn, cs, taup, cutv, ops, stl, gw);
+    split_layer_kernel<<<(unsigned)(ga < cap ? ga : cap), 128, 0, stream>>>(p, c0, cn, cs, taup, y0b, cutv, ops, stl, gw);
 #if B200_HAVE_TEAM
     if (team) {
       const unsigned gt = (unsigned)((cn + 31) / 32);  // 4 warps x 8 solves per CTA
