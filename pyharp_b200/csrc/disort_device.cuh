@@ -354,6 +354,9 @@ B200_HD void ws_prefetch_record(const double* wsl, int lev, long tid) {
 #ifndef B200_TMA_BACK
 #define B200_TMA_BACK 1
 #endif
+#ifndef B200_EXP_HALFREC
+#define B200_EXP_HALFREC 0
+#endif
 template <int NSAVE>
 struct TmaRing {
   // stages: what fits 150-200 KB of shared memory per SM at the kernel's residency (8 warps/SM at nn = 4,
@@ -365,6 +368,11 @@ struct TmaRing {
 #endif
   static constexpr int kRecDoubles = NSAVE * kWsLanes;
   static constexpr int kRecBytes = kRecDoubles * 8;
+  // profiling experiment only (-DB200_EXP_HALFREC=1, never in the product build): elements e >= kLiveElems of a record are
+  // neither stored nor copied (the back sweep re-uses element e % kLiveElems) -- same instructions, half the workspace
+  // traffic, wrong fluxes: what cutting the back-sweep records in half could buy at most (profiles/r02/sweeps.md, e42)
+  static constexpr int kLiveElems = B200_EXP_HALFREC ? (NSAVE + 1) / 2 : NSAVE;
+  static constexpr int kCopyBytes = kLiveElems * kWsLanes * 8;
   static constexpr int kWarpDoubles = kStages * kRecDoubles + 16;  // + 128 bytes: the stage barriers
   static constexpr bool kUsed = B200_TMA_BACK && NSAVE <= 32;
 };

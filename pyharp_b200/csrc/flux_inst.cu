@@ -204,6 +204,10 @@ cudaError_t launch_warp(const SolveParams& p, unsigned grid, int block, cudaStre
 #ifndef B200_SPLIT_Y0BUF
 #define B200_SPLIT_Y0BUF 1
 #endif
+// threads per CTA of the layer kernel (the CTA walks its items in lockstep)
+#ifndef B200_SPLIT_BLOCK_A
+#define B200_SPLIT_BLOCK_A 128
+#endif
 #ifndef B200_SPLIT_MINB_A
 #define B200_SPLIT_MINB_A 1
 #endif
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(128) split_prefix_kernel(SolveParams p, long c
 }
 
 // (gw = solves per group of the hand-over buffer: kWsLanes for the thread form of the adding phase, kGrp for the team form)
-__global__ void __launch_bounds__(128, B200_SPLIT_MINB_A) split_layer_kernel(SolveParams p, long c0, long cn, long cs,
+__global__ void __launch_bounds__(B200_SPLIT_BLOCK_A, B200_SPLIT_MINB_A) split_layer_kernel(SolveParams p, long c0, long cn, long cs,
                                                                               const double* taup, const double* y0b,
                                                                               const int* cutv, double* ops, int* stl, int gw) {
   constexpr int NN = B200_NN, NOPS = kOpsDoubles<NN>;
@@ -320,9 +324,13 @@ cudaError_t launch_split(const SolveParams& p, long chunk, int sm_count, cudaStr
   double* rec = ops + (size_t)cs * nlyr * kOpsDoubles<B200_NN>;
   int* cutv = reinterpret_cast<int*>(rec + (size_t)cs * nlyr * kNsave);
   int* stl = cutv + cs;
+  // (experiment build -DB200_SMEM_Y=1: the Jacobi eigenvector accumulator of every thread in shared memory)
+  constexpr size_t kLayerSmem = B200_SMEM_Y ? (size_t)B200_NN * B200_NN * B200_SPLIT_BLOCK_A * sizeof(double) : 0;
   static int occ_a = 0;
   if (occ_a == 0) {
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, split_layer_kernel, 128, 0);
+    cudaError_t e = cudaSuccess;
+    if (kLayerSmem > 48 * 1024) e = cudaFuncSetAttribute(split_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLayerSmem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, split_layer_kernel, B200_SPLIT_BLOCK_A, kLayerSmem);
     if (e != cudaSuccess) return e;
     if (occ_a < 1) occ_a = 1;
   }
@@ -344,8 +352,8 @@ cudaError_t launch_split(const SolveParams& p, long chunk, int sm_count, cudaStr
     const long cn = (p.nlocal - c0 < cs) ? p.nlocal - c0 : cs;
     const unsigned gs = (unsigned)((cn + 127) / 128);
     split_prefix_kernel<<<gs, 128, 0, stream>>>(p, c0, cn, cs, taup, y0b, cutv, stl);
-    const long ga = (cn * nlyr + 127) / 128, cap = (long)sm_count * occ_a;
-    split_layer_kernel<<<(unsigned)(ga < cap ? ga : cap), 128, 0, stream>>>(p, c0, cn, cs, taup, y0b, cutv, ops, stl, gw);
+    const long ga = (cn * nlyr + B200_SPLIT_BLOCK_A - 1) / B200_SPLIT_BLOCK_A, cap = (long)sm_count * occ_a;
+    split_layer_kernel<<<(unsigned)(ga < cap ? ga : cap), B200_SPLIT_BLOCK_A, kLayerSmem, stream>>>(p, c0, cn, cs, taup, y0b, cutv, ops, stl, gw);
 #if B200_HAVE_TEAM
     if (team) {
       const unsigned gt = (unsigned)((cn + 31) / 32);  // 4 warps x 8 solves per CTA
