@@ -52,7 +52,7 @@ GCM_SEED_COLS = 2048  # the full-size GCM batch tiles a seeded block of this man
 TRAFFIC = os.path.join(ROOT, "profiles", "r02", "traffic.json")
 HASHED = ["pyharp_b200/csrc/disort_solver_body.inc", "pyharp_b200/csrc/disort_layer_ops.inc",
           "pyharp_b200/csrc/disort_adding_step.inc", "pyharp_b200/csrc/disort_device.cuh",
-          "pyharp_b200/csrc/flux_inst.cu", "pyharp_b200/workloads.py"]
+          "pyharp_b200/csrc/flux_inst.cu", "pyharp_b200/csrc/adding_team.cuh", "pyharp_b200/workloads.py"]
 
 
 def parse():
@@ -364,7 +364,10 @@ def solver_step_bench(ctx, name, nwave, ncol, nlyr, steps, warmup, variant=0, ti
     kernel_ms = st["solve_kernel_ms"] / max(1, st["solves_timed"])
     nsolve = nwave * ncol
     out = {"nsolve": nsolve, "ms": ms, "ms_max": ms_max, "kernel_ms": kernel_ms, "clocks": clk, "wl": wl, "ds": ds,
-           "launches_per_step": 2 + (1 if wl.thermal else 0), "workspace_bytes": st["workspace_bytes"], "nprop": wl.shape[3],
+           # (the handle counts its launches per call: one solve kernel, or -- layer-split form, nstr >= 16 -- three per chunk)
+           "launches_per_step": max(2 + (1 if wl.thermal else 0), int(st.get("kernel_launches", 0)) + 1),
+           "kernel_name": "disort_flux_kernel" if wl.nstr < 16 else "split_prefix_kernel + split_layer_kernel + team_adding_kernel (per chunk)",
+           "workspace_bytes": st["workspace_bytes"], "nprop": wl.shape[3],
            "prop_bytes": d_prop.numel() * 8}
     if e2e_steps:
         h_prop = torch.from_numpy(wl.prop).pin_memory()
@@ -463,7 +466,7 @@ def main():
                               "ncol_per_gpu": ncol, "sharding": f"columns x{world}, no data-path collective",
                               "l2": "inputs (%.0f MB) and back-sweep workspace exceed the 126 MB L2; no explicit flush" % (r["prop_bytes"] / 1e6)},
                    "clocks": r["clocks"], "gpu_launches": (r["launches_per_step"] + 1) * steps,
-                   "kernel": {"name": "disort_flux_kernel", "avg_ms": r["kernel_ms"], "share_of_step": r["kernel_ms"] / (r["ms"] / steps),
+                   "kernel": {"name": r["kernel_name"], "avg_ms": r["kernel_ms"], "share_of_step": r["kernel_ms"] / (r["ms"] / steps),
                               "workspace_bytes": r["workspace_bytes"]},
                    "roofline": roofline_of(args.workload, wl.flops_per_solve(), wl.bytes_per_solve(), r["nsolve"], r["kernel_ms"],
                                            fp64_peak, hbm_peak, hbm_src),

@@ -14,15 +14,24 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 
-def counters(rep, kernel_regex="disort_flux_kernel"):
+KERNELS = ("disort_flux_kernel", "split_prefix_kernel", "split_layer_kernel", "team_adding_kernel", "split_adding_kernel")
+
+
+def counters(rep):
+    """one record per solve kernel in the capture: the fused kernel, or the kernels of one chunk of the layer-split form
+    (first launch of each)"""
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     h, u = rows[0], rows[1]
+    found = {}
     for v in rows[2:]:
         m = {n: (v[i], u[i]) for i, n in enumerate(h)}
-        if kernel_regex in m["Kernel Name"][0]:
-            return m
-    raise SystemExit(f"{rep}: no {kernel_regex} launch")
+        for k in KERNELS:
+            if k in m["Kernel Name"][0] and k not in found:
+                found[k] = m
+    if not found:
+        raise SystemExit(f"{rep}: no solve kernel launch")
+    return found
 
 
 def num(m, k):
@@ -31,7 +40,7 @@ def num(m, k):
 
 def main():
     tag = sys.argv[1]
-    out = {"comment": "per-launch counters of disort_flux_kernel from the ncu --set full captures of round 2 (profiles/r02/ncu_full_*_"
+    out = {"comment": "per-launch counters of the solve kernel (nstr = 16: of the three kernels of one chunk of the layer-split form, summed) from the ncu --set full captures of round 2 (profiles/r02/ncu_full_*_"
                       + tag + "_summary.txt): DRAM bytes = dram__bytes_read.sum + dram__bytes_write.sum; executed flop = 2 DFMA + DMUL "
                       "+ DADD thread instructions; FP64 pipe = sm__pipe_fp64_cycles_active.  `hash` = sha256 of the kernel sources and "
                       "the workload generator (bench.py: HASHED); bench.py ignores the file when it does not match",
@@ -41,15 +50,24 @@ def main():
         name, rest = arg.split("=")
         rep, nsolve = rest.rsplit(":", 1)
         nsolve = float(nsolve)
-        m = counters(rep)
-        cyc = num(m, "sm__cycles_elapsed.avg")
-        flop = sum(w * num(m, f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed") * cyc
-                   for op, w in (("dfma", 2), ("dmul", 1), ("dadd", 1)))
-        rd = num(m, "dram__bytes_read.sum") * unit[m["dram__bytes_read.sum"][1]]
-        wr = num(m, "dram__bytes_write.sum") * unit[m["dram__bytes_write.sum"][1]]
-        out[name] = {"bytes_per_launch": rd + wr, "solves_per_launch": nsolve, "executed_flop_per_solve": round(flop / nsolve, 1),
-                     "fp64_pipe_active_pct": round(num(m, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"), 1),
+        flop = byt = dur = pipe = 0.0
+        parts = {}
+        for k, m in counters(rep).items():
+            cyc = num(m, "sm__cycles_elapsed.avg")
+            f = sum(w * num(m, f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed") * cyc
+                    for op, w in (("dfma", 2), ("dmul", 1), ("dadd", 1)))
+            b = (num(m, "dram__bytes_read.sum") * unit[m["dram__bytes_read.sum"][1]]
+                 + num(m, "dram__bytes_write.sum") * unit[m["dram__bytes_write.sum"][1]])
+            t = num(m, "gpu__time_duration.sum") * {"ns": 1e-6, "us": 1e-3, "ms": 1.0}[m["gpu__time_duration.sum"][1]]
+            pk = num(m, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active")
+            flop, byt, dur, pipe = flop + f, byt + b, dur + t, pipe + pk * t
+            parts[k] = {"ms_under_ncu": round(t, 3), "executed_flop_per_solve": round(f / nsolve, 1), "bytes_per_solve": round(b / nsolve, 1),
+                        "fp64_pipe_active_pct": round(pk, 1)}
+        out[name] = {"bytes_per_launch": byt, "solves_per_launch": nsolve, "executed_flop_per_solve": round(flop / nsolve, 1),
+                     "fp64_pipe_active_pct": round(pipe / dur, 1),  # (time-weighted over the kernels of the solve)
                      "capture": f"profiles/r02/ncu_full_{name}_{tag}_summary.txt"}
+        if len(parts) > 1:
+            out[name]["kernels"] = parts
     json.dump(out, open(os.path.join(ROOT, "profiles", "r02", "traffic.json"), "w"), indent=1)
     print(json.dumps(out, indent=1))
 
