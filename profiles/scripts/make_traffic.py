@@ -18,8 +18,8 @@ KERNELS = ("disort_flux_kernel", "split_prefix_kernel", "split_layer_kernel", "t
 
 
 def counters(rep):
-    """one record per solve kernel in the capture: the fused kernel, or the kernels of one chunk of the layer-split form
-    (first launch of each)"""
+    """the launches of every solve kernel in the capture: one launch of the fused kernel, or the launches of all chunks
+    of one step of the layer-split form (their counters are summed)"""
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     h, u = rows[0], rows[1]
@@ -27,8 +27,8 @@ def counters(rep):
     for v in rows[2:]:
         m = {n: (v[i], u[i]) for i, n in enumerate(h)}
         for k in KERNELS:
-            if k in m["Kernel Name"][0] and k not in found:
-                found[k] = m
+            if k in m["Kernel Name"][0]:
+                found.setdefault(k, []).append(m)
     if not found:
         raise SystemExit(f"{rep}: no solve kernel launch")
     return found
@@ -52,17 +52,23 @@ def main():
         nsolve = float(nsolve)
         flop = byt = dur = pipe = 0.0
         parts = {}
-        for k, m in counters(rep).items():
-            cyc = num(m, "sm__cycles_elapsed.avg")
-            f = sum(w * num(m, f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed") * cyc
-                    for op, w in (("dfma", 2), ("dmul", 1), ("dadd", 1)))
-            b = (num(m, "dram__bytes_read.sum") * unit[m["dram__bytes_read.sum"][1]]
-                 + num(m, "dram__bytes_write.sum") * unit[m["dram__bytes_write.sum"][1]])
-            t = num(m, "gpu__time_duration.sum") * {"ns": 1e-6, "us": 1e-3, "ms": 1.0}[m["gpu__time_duration.sum"][1]]
-            pk = num(m, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active")
-            flop, byt, dur, pipe = flop + f, byt + b, dur + t, pipe + pk * t
-            parts[k] = {"ms_under_ncu": round(t, 3), "executed_flop_per_solve": round(f / nsolve, 1), "bytes_per_solve": round(b / nsolve, 1),
-                        "fp64_pipe_active_pct": round(pk, 1)}
+        for k, ms in counters(rep).items():
+            f = b = t = pk = 0.0
+            for m in ms:
+                if "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum" in m:  # (--metrics capture: plain counts)
+                    f += sum(w * num(m, f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum") for op, w in (("dfma", 2), ("dmul", 1), ("dadd", 1)))
+                else:
+                    cyc = num(m, "sm__cycles_elapsed.avg")
+                    f += sum(w * num(m, f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed") * cyc
+                             for op, w in (("dfma", 2), ("dmul", 1), ("dadd", 1)))
+                b += (num(m, "dram__bytes_read.sum") * unit[m["dram__bytes_read.sum"][1]]
+                      + num(m, "dram__bytes_write.sum") * unit[m["dram__bytes_write.sum"][1]])
+                ti = num(m, "gpu__time_duration.sum") * {"ns": 1e-6, "us": 1e-3, "ms": 1.0}[m["gpu__time_duration.sum"][1]]
+                t += ti
+                pk += num(m, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active") * ti
+            flop, byt, dur, pipe = flop + f, byt + b, dur + t, pipe + pk
+            parts[k] = {"launches": len(ms), "ms_under_ncu": round(t, 3), "executed_flop_per_solve": round(f / nsolve, 1),
+                        "bytes_per_solve": round(b / nsolve, 1), "fp64_pipe_active_pct": round(pk / t, 1)}
         out[name] = {"bytes_per_launch": byt, "solves_per_launch": nsolve, "executed_flop_per_solve": round(flop / nsolve, 1),
                      "fp64_pipe_active_pct": round(pipe / dur, 1),  # (time-weighted over the kernels of the solve)
                      "capture": f"profiles/r02/ncu_full_{name}_{tag}_summary.txt"}

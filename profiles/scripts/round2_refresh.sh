@@ -22,9 +22,13 @@ for w in amars_sw lbl; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:disort_flux_kernel -s 3 -c 1 -f -o $out/prof_${w}_$tag \
     python bench.py --workload $w --steps 2 --warmup 3 --no-cpu --no-e2e > $out/ncu_full_${w}_$tag.log 2>&1; echo "ncu full $w rc=$?"
 done
-# nstr = 16 runs the layer-split form: 7 chunks x 3 kernels per step at 16384 columns; skip the 3 warm-up steps, capture one chunk
+# nstr = 16 runs the layer-split form: 7 chunks x 3 kernels per step at 16384 columns (the chunks differ: other spectral
+# points); skip the 3 warm-up steps; --set full of the first chunk, then the counters of traffic.json over the 21 launches of a step
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"split_prefix|split_layer|team_adding" -s 63 -c 3 -f -o $out/prof_gcm_$tag \
   python bench.py --workload gcm --ncol 16384 --steps 2 --warmup 3 --no-cpu --no-e2e > $out/ncu_full_gcm_$tag.log 2>&1; echo "ncu full gcm rc=$?"
+timeout 900 ncu --metrics gpu__time_duration.sum,sm__cycles_elapsed.avg,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum \
+  --clock-control none -k regex:"split_prefix|split_layer|team_adding" -s 63 -c 21 -f -o $out/prof_gcm_step_$tag \
+  python bench.py --workload gcm --ncol 16384 --steps 2 --warmup 3 --no-cpu --no-e2e > $out/ncu_step_gcm_$tag.log 2>&1; echo "ncu step gcm rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"split_|team_" -c 120 --csv --log-file $out/launches_gcm_$tag.csv \
   python bench.py --workload gcm --ncol 16384 --steps 2 --warmup 3 --no-cpu --no-e2e > /dev/null 2>&1; echo "ncu launches gcm rc=$?"
 tail -3 $out/pytest_gpu_$tag.log
