@@ -28,6 +28,11 @@
 
 namespace b200 {
 
+// stage buffers for the hand-over records per warp (the record is copied to registers at the top of a layer, so one buffer
+// already gives the copy of the next layer a whole layer of arithmetic; two: e43)
+#ifndef B200_TEAM_STAGES
+#define B200_TEAM_STAGES 2
+#endif
 constexpr int kTeam = 4;            // lanes per solve
 constexpr int kGrp = 32 / kTeam;    // solves per warp = solves per group of the hand-over / record buffers
 
@@ -40,13 +45,17 @@ struct TeamLayout {
   static constexpr int kPivDoubles = 2 * NN + 2;          // pivot row: A part (NN) | right-hand sides (NN + 1) | pad
   static constexpr int kRaOff = 0;                        // Ra | da            NN rows x RS
   static constexpr int kXOff = NN * RS;                   // M1 | v1            NN rows x RS
-  static constexpr int kPivOff = 2 * NN * RS;             // two buffers of (R == 2: two) pivot rows
-  static constexpr int kTeamRaw = 2 * NN * RS + (R == 2 ? 4 : 2) * kPivDoubles;
+  // the pivot rows of the elimination (two buffers of -- R == 2 -- two rows) share the storage of M1 | v1, which is written
+  // after the elimination (one warp barrier in between)
+  static constexpr int kPivOff = kXOff;
+  static constexpr int kTeamRaw = 2 * NN * RS;
+  static_assert((R == 2 ? 4 : 2) * kPivDoubles <= NN * RS, "pivot rows fit the M1 | v1 slab");
   // team stride: an odd number of 16-byte chunks (mod 8 chunks = 128 bytes)
   static constexpr int kTeamDoubles = ((kTeamRaw / 2) % 2 == 1) ? kTeamRaw : kTeamRaw + 2;
   static constexpr int kStageDoubles = NOPS * kGrp;       // one layer of the warp's group
   static constexpr int kStageBytes = kStageDoubles * 8;
-  static constexpr int kWarpDoubles = 2 * kStageDoubles + 2 + kGrp * kTeamDoubles;  // stages | 2 barriers | slabs
+  static constexpr int kStages = B200_TEAM_STAGES;
+  static constexpr int kWarpDoubles = kStages * kStageDoubles + 2 + kGrp * kTeamDoubles;  // stages | 2 barriers | slabs
   static_assert(kStageBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
   static_assert(kWarpDoubles % 2 == 0 && kTeamDoubles % 2 == 0 && RS % 2 == 0, "16-byte alignment of the slabs");
 };
@@ -70,8 +79,9 @@ __device__ __forceinline__ void team_adding_sweep(const SolveParams& p, const QT
 
   double* wbase = smem + (size_t)wid * L::kWarpDoubles;
   double* stage0 = wbase;
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(wbase + 2 * L::kStageDoubles);
-  double* slab = wbase + 2 * L::kStageDoubles + 2 + (size_t)tj * L::kTeamDoubles;
+  constexpr int S = L::kStages;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(wbase + S * L::kStageDoubles);
+  double* slab = wbase + S * L::kStageDoubles + 2 + (size_t)tj * L::kTeamDoubles;
   double* RaS = slab + L::kRaOff;
   double* Xs = slab + L::kXOff;
   double* Pv = slab + L::kPivOff;
@@ -98,7 +108,7 @@ __device__ __forceinline__ void team_adding_sweep(const SolveParams& p, const QT
   double* rec_g = rec + grp * ((long)nlyr * NSAVE * kGrp) + tj;
   if (lane == 0) {
     if (ncw > 0) b200_tma_load(stage0, ops_g, L::kStageBytes, bars);
-    if (ncw > 1) b200_tma_load(stage0 + L::kStageDoubles, ops_g + (long)NOPS * kGrp, L::kStageBytes, bars + 1);
+    if (S > 1 && ncw > 1) b200_tma_load(stage0 + L::kStageDoubles, ops_g + (long)NOPS * kGrp, L::kStageBytes, bars + 1);
   }
 
   // rows of this lane, their packed-symmetric offsets and stream scalings
@@ -129,8 +139,8 @@ __device__ __forceinline__ void team_adding_sweep(const SolveParams& p, const QT
   const double fb = cm.umu0 * cm.fbeam;
   for (int lc = 0; lc < ncw; ++lc) {
     const bool act = lc < ncut;
-    const int buf = lc & 1;
-    b200_mbar_wait(bars + buf, (unsigned)(lc >> 1) & 1u);
+    const int buf = lc % S;
+    b200_mbar_wait(bars + buf, (unsigned)(lc / S) & 1u);
     const double* sg = stage0 + buf * L::kStageDoubles + tj;
     double rl[R][NN], tl[R][NN], spv[R], smv[R];
 #pragma unroll
@@ -145,9 +155,9 @@ __device__ __forceinline__ void team_adding_sweep(const SolveParams& p, const QT
     }
     const double etop = sg[(2 * NS + 2 * NN) * kGrp];
     if (act) ebot_last = sg[(2 * NS + 2 * NN + 1) * kGrp];
-    __syncwarp();  // every lane has taken its values out of the stage: refill it with layer lc + 2
-    if (lane == 0 && lc + 2 < ncw)
-      b200_tma_load(stage0 + buf * L::kStageDoubles, ops_g + (long)(lc + 2) * NOPS * kGrp, L::kStageBytes, bars + buf);
+    __syncwarp();  // every lane has taken its values out of the stage: refill it with layer lc + S
+    if (lane == 0 && lc + S < ncw)
+      b200_tma_load(stage0 + buf * L::kStageDoubles, ops_g + (long)(lc + S) * NOPS * kGrp, L::kStageBytes, bars + buf);
 
     // ---- A = I - R Ra, right-hand sides [T | R da + s+]; and TR = T Ra, td = T da for the stack update below
     double A[R][NN], B[R][NN + 1], TR[R][NN], td[R];
@@ -308,6 +318,7 @@ __device__ __forceinline__ void team_adding_sweep(const SolveParams& p, const QT
       }
     }
 
+    __syncwarp();  // (the last pivot rows have been read: their storage takes M1 | v1)
     // ---- new stack: Ra' = R + T Ra M1 = R + TR M1,  da' = s- + T (da + Ra v1) = s- + T da + TR v1  (TR = T Ra and T da were
     //      formed with the rows of Ra | da read for A above: one broadcast of [M1 | v1] instead of two exchanges)
 #pragma unroll

@@ -21,6 +21,9 @@
 #if B200_HAVE_TEAM
 #include "adding_team.cuh"
 #endif
+#ifndef B200_TEAM_MINB
+#define B200_TEAM_MINB 2  // resident CTAs per SM asked of ptxas for the team adding kernel
+#endif
 
 #ifndef B200_NN
 #error "compile with -DB200_NN=<nstr/2>"
@@ -208,6 +211,12 @@ cudaError_t launch_warp(const SolveParams& p, unsigned grid, int block, cudaStre
 #ifndef B200_SPLIT_BLOCK_A
 #define B200_SPLIT_BLOCK_A 128
 #endif
+// L2 prefetch of the next item's inputs in the layer kernel: measured 2 % SLOWER (profiles/r02/sweeps.md, e44 -- the other
+// resident CTA already covers the item-start loads), so it is off
+#ifndef B200_SPLIT_PREFETCH
+#define B200_SPLIT_PREFETCH 0
+#endif
+__device__ __forceinline__ void b200_prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 #ifndef B200_SPLIT_MINB_A
 #define B200_SPLIT_MINB_A 1
 #endif
@@ -268,6 +277,26 @@ __global__ void __launch_bounds__(B200_SPLIT_BLOCK_A, B200_SPLIT_MINB_A) split_l
     lc += dl;
     i += di;
     if (i >= cn) { i -= cn; ++lc; }
+#if B200_SPLIT_PREFETCH
+    // the inputs of this thread's NEXT item are pulled into the L2 behind this item's arithmetic: every item starts with a
+    // dozen dependent-free global loads (cut-off level, optical depth at the layer top, boundary fields, Legendre
+    // polynomials, the layer's prop record), and in lockstep all warps of the CTA wait for them at the same time
+    if (t + nthreads < items) {
+      const long sn = c0 + i;
+      b200_prefetch_l2(cutv + i);
+      b200_prefetch_l2(taup + (long)lc * cs + i);
+      if (p.umu0) b200_prefetch_l2(p.umu0 + (p.bc_bcast ? 0 : sn));
+      if (p.fbeam) b200_prefetch_l2(p.fbeam + (p.bc_bcast ? 0 : sn));
+      if (p.albedo) b200_prefetch_l2(p.albedo + (p.bc_bcast ? 0 : sn));
+      const double* qn = p.prop + sn * nlyr * p.nprop + (long)(nlyr - 1 - lc) * p.nprop;
+      b200_prefetch_l2(qn);
+      if (p.nprop > 16) b200_prefetch_l2(qn + 16);
+      if (B200_SPLIT_Y0BUF && p.fbeam) {
+#pragma unroll
+        for (int l = 0; l < 2 * NN; ++l) b200_prefetch_l2(y0b + (long)l * cs + i);
+      }
+    }
+#endif
     const bool active = in && lcc < (cutv[ic] & 0xffff);  // layers below the cut-off are not examined
     if (!__any_sync(0xffffffffu, active)) continue;
     const long s = c0 + ic;
@@ -301,7 +330,7 @@ __global__ void __launch_bounds__(128, B200_SPLIT_MINB_B) split_adding_kernel(So
 
 #if B200_HAVE_TEAM
 template <int BAND>
-__global__ void __launch_bounds__(128, 2) team_adding_kernel(SolveParams p, long c0, long cn, const int* cutv, const int* stl,
+__global__ void __launch_bounds__(128, B200_TEAM_MINB) team_adding_kernel(SolveParams p, long c0, long cn, const int* cutv, const int* stl,
                                                              const double* ops, double* rec) {
   extern __shared__ __align__(128) double b200_smem[];
   team_adding_sweep<B200_NN, BAND>(p, c_qt, c0, cn, cutv, stl, ops, rec, b200_smem);
@@ -339,12 +368,16 @@ cudaError_t launch_split(const SolveParams& p, long chunk, int sm_count, cudaStr
   static const bool team = B200_HAVE_TEAM && !(std::getenv("B200DISORT_TEAM") && std::atoi(std::getenv("B200DISORT_TEAM")) == 0);
 #if B200_HAVE_TEAM
   constexpr size_t kTeamSmem = (size_t)4 * TeamLayout<B200_NN>::kWarpDoubles * sizeof(double);
-  static bool attr_set = false;
-  if (team && !attr_set) {
+  // (function attributes are per device: a C++ host that drives every GPU of the box from one process reaches this with
+  // each of them current)
+  static bool attr_set[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (team && !attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(team_adding_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTeamSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(team_adding_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTeamSmem);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[dev] = true;
   }
 #endif
   const int gw = team ? 32 / 4 : kWsLanes;
