@@ -407,6 +407,21 @@ def nccl_selfcheck(ctx):
             "what": "spectral-point sharding + b200disort_allreduce_band == single-GPU band flux"}
 
 
+class stdout_to_stderr:
+    """file descriptor 1 -> 2 for the duration of the block (C libraries write to the descriptor, not to sys.stdout)"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -425,7 +440,11 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # rank 0's stdout carries ONE JSON line: NCCL's version banner (printed at the first communicator when the box
+        # sets NCCL_DEBUG=VERSION) goes to stderr
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
 
     from pyharp_b200 import fp64_peak_tflops, workloads as W
     ctx = Ctx()
