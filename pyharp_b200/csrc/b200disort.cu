@@ -306,15 +306,54 @@ static int ring_end(b200disort_handle* h, cudaStream_t stream) {
   return B200DISORT_OK;
 }
 
-// which stream counts take the layer-split form by default (measured, profiles/r02/sweeps.md e36: nstr = 12 loses 14 %,
-// nstr = 16 / 24 / 32 gain 1.3-1.9x / 1.3x / 2x)
-static int split_default(int nn) { return nn >= 8 ? 1 : 0; }
+// Layer-split form by default (measured, profiles/r02/sweeps.md e36, e45): from nstr = 16 up (nstr = 12 loses 14 %, nstr = 16 /
+// 24 / 32 gain 1.3-1.9x / 1.3x / 2x), and at nstr = 8 for batches above the warp-per-solve form's range of at most this many
+// solves (1184 < n <= 8192: 0.14-0.21 ms per call against 0.23 ms for the fused kernel)
+static const long kSplitSmallMax = 8192;
 
 // Launch the flux kernel for p.nlocal solves on `stream` with the given back-sweep workspace.
 // timed = record the launch in the handle's event ring (handle stream only).
 int b200::launch_flux(b200disort_handle* h, SolveParams& p, cudaStream_t stream, double** ws, size_t* ws_bytes,
                       bool timed) {
   const FluxInst* inst = h->inst;
+  // Layer-split form (flux_inst.cu): layer phase as one thread per (solve, layer), adding recursion + back sweep as a second
+  // kernel (teams of four lanes per solve at nstr = 8 / 16), chunk by chunk through a scratch buffer.  It is the default
+  // from nstr = 16 up (the fused kernel spills there) and, at nstr = 8, for batches far below one resident wave of the fused
+  // kernel -- pyharp's own calls are 500 x 1 and G x 1 solves, and the layer phase has nlyr times the parallelism of the
+  // batch.  B200DISORT_SPLIT / the handle's layer_split: 0 = never, 1 = always, -1 = that default;
+  // B200DISORT_SPLIT_SMALL_MAX = largest nstr = 8 batch that takes it; B200DISORT_SPLIT_CHUNK = solves per chunk
+  // (default: two resident waves of the adding kernel).
+  if (inst->launch_split) {
+    static const int env_split = std::getenv("B200DISORT_SPLIT") ? std::atoi(std::getenv("B200DISORT_SPLIT")) : -1;
+    static const long env_chunk = std::getenv("B200DISORT_SPLIT_CHUNK") ? std::atol(std::getenv("B200DISORT_SPLIT_CHUNK")) : 0;
+    static const long env_small = std::getenv("B200DISORT_SPLIT_SMALL_MAX") ? std::atol(std::getenv("B200DISORT_SPLIT_SMALL_MAX")) : -1;
+    const int mode = h->layer_split >= 0 ? h->layer_split : env_split;
+    // (nstr = 8: up to one resident wave of warps the warp-per-solve form below is faster still -- 0.12 against 0.13 ms per
+    // call -- and from ~10^4 solves on the fused kernel is; in between the split form is 1.1-1.5x faster than either)
+    static const long env_warp = std::getenv("B200DISORT_WARP_SOLVE_MAX") ? std::atol(std::getenv("B200DISORT_WARP_SOLVE_MAX")) : -1;
+    const long warp_max = h->warp_solve_max >= 0 ? h->warp_solve_max : env_warp >= 0 ? env_warp : (long)h->sm_count * 8;
+    const bool use = mode == 1 || (mode < 0 && (inst->nn >= 8 || (inst->nn == 4 && p.nlocal > warp_max &&
+                                                                  p.nlocal <= (env_small >= 0 ? env_small : kSplitSmallMax))));
+    if (use) {
+      long chunk = env_chunk > 0 ? env_chunk : (long)h->sm_count * 256 * 2;
+      chunk = std::min<long>(chunk, p.nlocal);
+      const size_t need = inst->split_scratch(p.nlyr, chunk);
+      int rc = ensure_dev(ws, ws_bytes, need);
+      if (rc != B200DISORT_OK) return rc;
+      if (timed) {
+        rc = ring_begin(h, stream);
+        if (rc != B200DISORT_OK) return rc;
+      }
+      CU_TRY(inst->launch_split(p, chunk, h->sm_count, stream, *ws));
+      if (timed) {
+        rc = ring_end(h, stream);
+        if (rc != B200DISORT_OK) return rc;
+      }
+      h->stats.kernel_launches += 3 * (int)((p.nlocal + chunk - 1) / chunk);
+      h->stats.workspace_bytes = *ws_bytes;
+      return B200DISORT_OK;
+    }
+  }
   // Batches far below one resident wave (pyharp's own calls: 500 x 1, G x 1 solves): the warp-per-solve form, whose
   // lanes take the layers of a solve -- a thread-per-solve launch would occupy a handful of SMs for as long as one
   // thread needs to walk the column.  One call of it lasts ~0.55x as long (profiles/r02/sweeps.md, e32), so it is used
@@ -344,34 +383,6 @@ int b200::launch_flux(b200disort_handle* h, SolveParams& p, cudaStream_t stream,
         if (rc != B200DISORT_OK) return rc;
       }
       h->stats.kernel_launches += 1;
-      h->stats.workspace_bytes = *ws_bytes;
-      return B200DISORT_OK;
-    }
-  }
-  // nstr >= 12: the layer-split form (flux_inst.cu) -- layer phase as one thread per (solve, layer), adding recursion as
-  // one thread per solve, chunk by chunk through a scratch buffer.  B200DISORT_SPLIT / the handle's layer_split: 0 = the
-  // fused kernel, 1 = the split form, -1 = default (per stream count, see split_default).  B200DISORT_SPLIT_CHUNK =
-  // solves per chunk (default: two resident waves of the adding kernel).
-  if (inst->launch_split) {
-    static const int env_split = std::getenv("B200DISORT_SPLIT") ? std::atoi(std::getenv("B200DISORT_SPLIT")) : -1;
-    static const long env_chunk = std::getenv("B200DISORT_SPLIT_CHUNK") ? std::atol(std::getenv("B200DISORT_SPLIT_CHUNK")) : 0;
-    const int mode = h->layer_split >= 0 ? h->layer_split : env_split >= 0 ? env_split : split_default(inst->nn);
-    if (mode != 0) {
-      long chunk = env_chunk > 0 ? env_chunk : (long)h->sm_count * 256 * 2;
-      chunk = std::min<long>(chunk, p.nlocal);
-      const size_t need = inst->split_scratch(p.nlyr, chunk);
-      int rc = ensure_dev(ws, ws_bytes, need);
-      if (rc != B200DISORT_OK) return rc;
-      if (timed) {
-        rc = ring_begin(h, stream);
-        if (rc != B200DISORT_OK) return rc;
-      }
-      CU_TRY(inst->launch_split(p, chunk, h->sm_count, stream, *ws));
-      if (timed) {
-        rc = ring_end(h, stream);
-        if (rc != B200DISORT_OK) return rc;
-      }
-      h->stats.kernel_launches += 3 * (int)((p.nlocal + chunk - 1) / chunk);
       h->stats.workspace_bytes = *ws_bytes;
       return B200DISORT_OK;
     }

@@ -15,8 +15,9 @@
 
 #include "flux_inst.cuh"
 // team form of the adding phase of the layer-split solve (four lanes per solve): nstr = 16
+// (and nstr = 8, where the split form serves batches far below one resident wave: pyharp's own 500 x 1 / G x 1 calls)
 #ifndef B200_HAVE_TEAM
-#define B200_HAVE_TEAM (B200_NN == 8)
+#define B200_HAVE_TEAM (B200_NN == 8 || B200_NN == 4)
 #endif
 #if B200_HAVE_TEAM
 #include "adding_team.cuh"
@@ -197,11 +198,13 @@ cudaError_t launch_warp(const SolveParams& p, unsigned grid, int block, cudaStre
 // traffic per layer and solve -- less than the spill traffic it removes -- and the layer phase has nlyr times the
 // parallelism of the batch, so small batches fill the GPU as well.
 // ---------------------------------------------------------------------------
-#if B200_NN >= 6
+#if B200_NN >= 6 || B200_NN == 4
 #define B200_HAVE_SPLIT 1
 #else
 #define B200_HAVE_SPLIT 0
 #endif
+// thread form of the adding phase (the team form replaces it where it exists; kept at nstr >= 12 for comparison)
+#define B200_HAVE_SPLIT_THREAD (B200_NN >= 6)
 #if B200_HAVE_SPLIT
 // Legendre polynomials at the beam angle: 1 = read from the prefix pass's buffer where they are used, 0 = recomputed per item
 #ifndef B200_SPLIT_Y0BUF
@@ -225,6 +228,7 @@ __device__ __forceinline__ void b200_prefetch_l2(const void* ptr) { asm volatile
 #endif
 constexpr int kSplitNoStatus = 0x7fffffff;
 
+template <bool NOMOM>
 __global__ void __launch_bounds__(128) split_prefix_kernel(SolveParams p, long c0, long cn, long cs, double* taup, double* y0b,
                                                            int* cutv, int* stl) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(128) split_prefix_kernel(SolveParams p, long c
     if (!cut && !planck && nlyr > 1 && ab >= 10.0) { ncut = lc; cut = true; }
     taup[(long)lc * cs + i] = tp;
     double dtp, dabs;
-    layer_depths_any<B200_NN, false>(p, pr, lc, dtp, dabs);
+    layer_depths_any<B200_NN, NOMOM>(p, pr, lc, dtp, dabs);
     tp += dtp;
     ab += dabs;
   }
@@ -257,6 +261,7 @@ __global__ void __launch_bounds__(128) split_prefix_kernel(SolveParams p, long c
 }
 
 // (gw = solves per group of the hand-over buffer: kWsLanes for the thread form of the adding phase, kGrp for the team form)
+template <bool NOMOM>
 __global__ void __launch_bounds__(B200_SPLIT_BLOCK_A, B200_SPLIT_MINB_A) split_layer_kernel(SolveParams p, long c0, long cn, long cs,
                                                                               const double* taup, const double* y0b,
                                                                               const int* cutv, double* ops, int* stl, int gw) {
@@ -304,12 +309,13 @@ __global__ void __launch_bounds__(B200_SPLIT_BLOCK_A, B200_SPLIT_MINB_A) split_l
     solve_common_any<NN>(p, c_qt, s, cm, false, !B200_SPLIT_Y0BUF);
     const double* pr = p.prop + s * nlyr * p.nprop;
     double* o = ops + (ic / gw) * ((long)nlyr * NOPS * gw) + (long)lcc * NOPS * gw + (ic % gw);
-    const int st = layer_ops_any<NN, false>(p, c_qt, cm, pr, lcc, taup[(long)lcc * cs + ic], o, gw,
+    const int st = layer_ops_any<NN, NOMOM>(p, c_qt, cm, pr, lcc, taup[(long)lcc * cs + ic], o, gw,
                                             B200_SPLIT_Y0BUF ? y0b + ic : nullptr, B200_SPLIT_Y0BUF ? cs : 1);
     if (active && st != ST_OK) atomicMin(stl + ic, st);  // (bad input < eigen failure < singular: status_merge's order)
   }
 }
 
+#if B200_HAVE_SPLIT_THREAD
 template <int BAND>
 __global__ void __launch_bounds__(128, B200_SPLIT_MINB_B) split_adding_kernel(SolveParams p, long c0, long cn, const int* cutv,
                                                                                const int* stl, const double* ops, double* rec) {
@@ -328,6 +334,7 @@ __global__ void __launch_bounds__(128, B200_SPLIT_MINB_B) split_adding_kernel(So
                              rec + blk * ((long)nlyr * kNsave * kWsLanes) + lane, kWsLanes, lane);
 }
 
+#endif
 #if B200_HAVE_TEAM
 template <int BAND>
 __global__ void __launch_bounds__(128, B200_TEAM_MINB) team_adding_kernel(SolveParams p, long c0, long cn, const int* cutv, const int* stl,
@@ -358,14 +365,15 @@ cudaError_t launch_split(const SolveParams& p, long chunk, int sm_count, cudaStr
   static int occ_a = 0;
   if (occ_a == 0) {
     cudaError_t e = cudaSuccess;
-    if (kLayerSmem > 48 * 1024) e = cudaFuncSetAttribute(split_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLayerSmem);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, split_layer_kernel, B200_SPLIT_BLOCK_A, kLayerSmem);
+    if (kLayerSmem > 48 * 1024) e = cudaFuncSetAttribute(split_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLayerSmem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, split_layer_kernel<false>, B200_SPLIT_BLOCK_A, kLayerSmem);
     if (e != cudaSuccess) return e;
     if (occ_a < 1) occ_a = 1;
   }
   const bool band = p.bflx_t != nullptr;
   // adding phase: team form (four lanes per solve) where it is instantiated; B200DISORT_TEAM=0 selects the thread form
-  static const bool team = B200_HAVE_TEAM && !(std::getenv("B200DISORT_TEAM") && std::atoi(std::getenv("B200DISORT_TEAM")) == 0);
+  static const bool team = B200_HAVE_TEAM && !(B200_HAVE_SPLIT_THREAD && std::getenv("B200DISORT_TEAM") && std::atoi(std::getenv("B200DISORT_TEAM")) == 0);
+  const bool nomom = B200_HAVE_NOMOM && p.nprop <= 2;
 #if B200_HAVE_TEAM
   constexpr size_t kTeamSmem = (size_t)4 * TeamLayout<B200_NN>::kWarpDoubles * sizeof(double);
   // (function attributes are per device: a C++ host that drives every GPU of the box from one process reaches this with
@@ -384,9 +392,19 @@ cudaError_t launch_split(const SolveParams& p, long chunk, int sm_count, cudaStr
   for (long c0 = 0; c0 < p.nlocal; c0 += cs) {
     const long cn = (p.nlocal - c0 < cs) ? p.nlocal - c0 : cs;
     const unsigned gs = (unsigned)((cn + 127) / 128);
-    split_prefix_kernel<<<gs, 128, 0, stream>>>(p, c0, cn, cs, taup, y0b, cutv, stl);
     const long ga = (cn * nlyr + B200_SPLIT_BLOCK_A - 1) / B200_SPLIT_BLOCK_A, cap = (long)sm_count * occ_a;
-    split_layer_kernel<<<(unsigned)(ga < cap ? ga : cap), B200_SPLIT_BLOCK_A, kLayerSmem, stream>>>(p, c0, cn, cs, taup, y0b, cutv, ops, stl, gw);
+    const unsigned gl = (unsigned)(ga < cap ? ga : cap);
+#if B200_HAVE_NOMOM
+    if (nomom) {
+      split_prefix_kernel<true><<<gs, 128, 0, stream>>>(p, c0, cn, cs, taup, y0b, cutv, stl);
+      split_layer_kernel<true><<<gl, B200_SPLIT_BLOCK_A, kLayerSmem, stream>>>(p, c0, cn, cs, taup, y0b, cutv, ops, stl, gw);
+    } else
+#endif
+    {
+      split_prefix_kernel<false><<<gs, 128, 0, stream>>>(p, c0, cn, cs, taup, y0b, cutv, stl);
+      split_layer_kernel<false><<<gl, B200_SPLIT_BLOCK_A, kLayerSmem, stream>>>(p, c0, cn, cs, taup, y0b, cutv, ops, stl, gw);
+    }
+    (void)nomom;
 #if B200_HAVE_TEAM
     if (team) {
       const unsigned gt = (unsigned)((cn + 31) / 32);  // 4 warps x 8 solves per CTA
@@ -395,8 +413,10 @@ cudaError_t launch_split(const SolveParams& p, long chunk, int sm_count, cudaStr
       continue;
     }
 #endif
+#if B200_HAVE_SPLIT_THREAD
     if (band) split_adding_kernel<1><<<gs, 128, 0, stream>>>(p, c0, cn, cutv, stl, ops, rec);
     else split_adding_kernel<0><<<gs, 128, 0, stream>>>(p, c0, cn, cutv, stl, ops, rec);
+#endif
   }
   return cudaGetLastError();
 }
@@ -469,7 +489,10 @@ cudaError_t launch(const SolveParams& p, unsigned grid, int block, cudaStream_t 
   return cudaGetLastError();
 }
 
-#if B200_HAVE_WARP
+#if B200_HAVE_WARP && B200_HAVE_SPLIT
+const FluxInst kInst = {B200_NN, B200_NN * B200_NN + 2 * B200_NN + 1, B200_MAX_THREADS, kCarryBack<B200_NN> ? 2 : 1, upload_tables, occupancy, launch,
+                        warp_scratch, warp_occupancy, launch_warp, split_scratch, launch_split};
+#elif B200_HAVE_WARP
 const FluxInst kInst = {B200_NN, B200_NN * B200_NN + 2 * B200_NN + 1, B200_MAX_THREADS, kCarryBack<B200_NN> ? 2 : 1, upload_tables, occupancy, launch,
                         warp_scratch, warp_occupancy, launch_warp, nullptr, nullptr};
 #elif B200_HAVE_SPLIT
