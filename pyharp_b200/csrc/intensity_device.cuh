@@ -89,6 +89,13 @@ B200_FN_ATTR inline IntensityWs intensity_ws_map(int nlyr, int nstr, int ntau, i
   return m;
 }
 
+// columns of at most this many layers run the per-layer phase CTA-cooperatively (one layer at a time) instead of one
+// thread per layer
+#ifndef B200_K3_COOP_MAX_LAYERS
+#define B200_K3_COOP_MAX_LAYERS 16
+#endif
+constexpr int kCoopMaxLayers = B200_K3_COOP_MAX_LAYERS;
+
 // header slots
 enum { H_STATUS = 0, H_NCUT, H_LYRCUT, H_NAZ, H_KCONV, H_DONE, H_TPLANK, H_BPLANK, H_SING };
 
@@ -194,8 +201,20 @@ B200_FN_ATTR inline bool jacobi_dyn(double* g, double* y, int n) {
 // (c_upisot) particular solutions, interpolation to user angles (c_terpev / c_terpso).
 // Returns a status code.
 // ------------------------------------------------------------------------------------------
-B200_FN_ATTR inline int intensity_layer(const IntensityParams& P, const IntensityWs& M, double* w, double* scr, int lc,
-                                        int mazim, bool planck, bool user_angles, double fbeam, double umu0) {
+//
+// Two execution shapes of the same statements (template COOP):
+//   COOP = false  one thread owns the layer (the CTA's threads take different layers): ltid = 0, lnthr = 1, no barriers;
+//   COOP = true   the whole CTA works on ONE layer -- for columns with fewer layers than threads (tests/test_disort.cpp
+//                 has a single layer: its per-layer phase ran on one thread while 63 waited, 2.1 ms per 10-solve call).
+//                 Loops over independent outputs are spread over the CTA (LFOR), the short factorisations (Cholesky
+//                 8 x 8, Jacobi, the 16 x 16 pivoted LU of c_upbeam / c_upisot) stay on one thread, CTA barriers separate
+//                 the phases.  `scr` holds the layer's matrices (shared by the CTA when COOP), `prv` this thread's own
+//                 vectors.  Every thread must call it with the same arguments.
+#define LFOR(i, n) for (int i = ltid; i < (n); i += lnthr)
+#define LSYNC() do { if (COOP) { B200_SYNC(); } } while (0)
+template <bool COOP>
+B200_FN_ATTR inline int intensity_layer(const IntensityParams& P, const IntensityWs& M, double* w, double* scr, double* prv, int lc,
+                                        int mazim, bool planck, bool user_angles, double fbeam, double umu0, int ltid, int lnthr) {
   const int N = P.nstr, nn = N / 2, U = P.numu;
   const double* gl = w + M.gl + (long)lc * N;
   const double* ylmc = w + M.ylmc;
@@ -206,54 +225,66 @@ B200_FN_ATTR inline int intensity_layer(const IntensityParams& P, const Intensit
   double* Pt = scr; double* Lq = Pt + nn * nn; double* G = Lq + nn * nn; double* Y = G + nn * nn;
   double* X = Y + nn * nn; double* Z = X + nn * nn;
   double* cc = Z + nn * nn; double* arr = cc + N * N;
-  double* zj = arr + N * N; double* z0 = zj + N; double* z1 = z0 + N; double* wk = z1 + N;  // wk: 2N+2
-  int* ipvt = reinterpret_cast<int*>(wk + 2 * N + 2);                                        // N ints <= N doubles
+  double* zj = arr + N * N; double* z0 = zj + N; double* z1 = z0 + N; double* wks = z1 + N;  // wks: 2N+2, shared
+  int* ipvt = reinterpret_cast<int*>(wks + 2 * N + 2);                                       // N ints <= N doubles
+  double* wk = prv + (wks - scr);  // this thread's own 2N+2 doubles (the same storage when !COOP)
   const double delm0 = (mazim == 0) ? 1.0 : 0.0;
   int st = ST_OK;
 
   // symmetric reduced matrices: Pt = diag(1/mu) - sum_{l-m odd} gl Yh Yh^T, Qt likewise over even l-m
-  for (int i = 0; i < nn; ++i)
-    for (int k = 0; k <= i; ++k) {
-      double so = 0.0, se = 0.0;
-      for (int l = mazim; l < N; ++l) {
-        const double v = gl[l] * ylmc[l * N + i] * ylmc[l * N + k];
-        if ((l - mazim) & 1) so += v; else se += v;
-      }
-      const double e = sqrt(P.cwt[i] / P.cmu[i]) * sqrt(P.cwt[k] / P.cmu[k]);
-      const double dg = (i == k) ? 1.0 / P.cmu[i] : 0.0;
-      Pt[i * nn + k] = Pt[k * nn + i] = dg - e * so;
-      Lq[i * nn + k] = Lq[k * nn + i] = dg - e * se;
+  LFOR(idx, nn * nn) {
+    const int i = idx / nn, k = idx - i * nn;
+    if (k > i) continue;
+    double so = 0.0, se = 0.0;
+    for (int l = mazim; l < N; ++l) {
+      const double v = gl[l] * ylmc[l * N + i] * ylmc[l * N + k];
+      if ((l - mazim) & 1) so += v; else se += v;
     }
-  // Cholesky Qt = L L^T (lower, in place)
-  for (int c = 0; c < nn; ++c) {
-    double d = Lq[c * nn + c];
-    for (int k = 0; k < c; ++k) d -= Lq[c * nn + k] * Lq[c * nn + k];
-    if (!(d > 0.0)) { st = ST_SINGULAR; d = 1.0; }
-    const double r = sqrt(d);
-    Lq[c * nn + c] = r;
-    for (int i = c + 1; i < nn; ++i) {
-      double v = Lq[i * nn + c];
-      for (int k = 0; k < c; ++k) v -= Lq[i * nn + k] * Lq[c * nn + k];
-      Lq[i * nn + c] = v / r;
-    }
-    for (int i = 0; i < c; ++i) Lq[i * nn + c] = 0.0;
+    const double e = sqrt(P.cwt[i] / P.cmu[i]) * sqrt(P.cwt[k] / P.cmu[k]);
+    const double dg = (i == k) ? 1.0 / P.cmu[i] : 0.0;
+    Pt[i * nn + k] = Pt[k * nn + i] = dg - e * so;
+    Lq[i * nn + k] = Lq[k * nn + i] = dg - e * se;
   }
-  // G = L^T Pt L  (X used as temporary Pt L)
-  for (int i = 0; i < nn; ++i)
+  LSYNC();
+  // Cholesky Qt = L L^T (lower, in place)
+  if (ltid == 0) {
     for (int c = 0; c < nn; ++c) {
-      double v = 0.0;
-      for (int k = c; k < nn; ++k) v += Pt[i * nn + k] * Lq[k * nn + c];
-      X[i * nn + c] = v;
+      double d = Lq[c * nn + c];
+      for (int k = 0; k < c; ++k) d -= Lq[c * nn + k] * Lq[c * nn + k];
+      if (!(d > 0.0)) { st = ST_SINGULAR; d = 1.0; }
+      const double r = sqrt(d);
+      Lq[c * nn + c] = r;
+      for (int i = c + 1; i < nn; ++i) {
+        double v = Lq[i * nn + c];
+        for (int k = 0; k < c; ++k) v -= Lq[i * nn + k] * Lq[c * nn + k];
+        Lq[i * nn + c] = v / r;
+      }
+      for (int i = 0; i < c; ++i) Lq[i * nn + c] = 0.0;
     }
-  for (int i = 0; i < nn; ++i)
-    for (int c = 0; c <= i; ++c) {
-      double v = 0.0;
-      for (int k = i; k < nn; ++k) v += Lq[k * nn + i] * X[k * nn + c];
-      G[i * nn + c] = G[c * nn + i] = v;
-    }
-  if (!jacobi_dyn(G, Y, nn) && st == ST_OK) st = ST_EIGEN_FAIL;
+  }
+  LSYNC();
+  // G = L^T Pt L  (X used as temporary Pt L)
+  LFOR(idx, nn * nn) {
+    const int i = idx / nn, c = idx - i * nn;
+    double v = 0.0;
+    for (int k = c; k < nn; ++k) v += Pt[i * nn + k] * Lq[k * nn + c];
+    X[i * nn + c] = v;
+  }
+  LSYNC();
+  LFOR(idx, nn * nn) {
+    const int i = idx / nn, c = idx - i * nn;
+    if (c > i) continue;
+    double v = 0.0;
+    for (int k = i; k < nn; ++k) v += Lq[k * nn + i] * X[k * nn + c];
+    G[i * nn + c] = G[c * nn + i] = v;
+  }
+  LSYNC();
+  if (ltid == 0) {
+    if (!jacobi_dyn(G, Y, nn) && st == ST_OK) st = ST_EIGEN_FAIL;
+  }
+  LSYNC();
   // X = L^-T Y, Z = L Y (columns = eigenmodes); s = T^-1 X, d = -T^-1 Z / k with T = sqrt(mu w)
-  for (int c = 0; c < nn; ++c) {
+  LFOR(c, nn) {
     for (int i = nn - 1; i >= 0; --i) {
       double v = Y[i * nn + c];
       for (int k = i + 1; k < nn; ++k) v -= Lq[k * nn + i] * X[k * nn + c];
@@ -265,71 +296,81 @@ B200_FN_ATTR inline int intensity_layer(const IntensityParams& P, const Intensit
       Z[i * nn + c] = v;
     }
   }
-  for (int jq = 0; jq < nn; ++jq) {
+  LSYNC();
+  LFOR(idx, nn * nn) {
+    const int jq = idx / nn, iq = idx - jq * nn;
     double lam = G[jq * nn + jq];
     if (!(lam > 0.0)) { if (st == ST_OK) st = ST_EIGEN_FAIL; lam = 1.0; }
     const double k = sqrt(lam);
-    kk[jq + nn] = k;
-    kk[nn - 1 - jq] = -k;
-    for (int iq = 0; iq < nn; ++iq) {
-      const double rt = 1.0 / sqrt(P.cmu[iq] * P.cwt[iq]);
-      const double s = rt * X[iq * nn + jq], d = -rt * Z[iq * nn + jq] / k;
-      const double up = 0.5 * (s + d), dn = 0.5 * (s - d);
-      gc[(iq + nn) * N + jq + nn] = up;
-      gc[(nn - 1 - iq) * N + jq + nn] = dn;
-      gc[(iq + nn) * N + nn - 1 - jq] = dn;
-      gc[(nn - 1 - iq) * N + nn - 1 - jq] = up;
+    if (iq == 0) {
+      kk[jq + nn] = k;
+      kk[nn - 1 - jq] = -k;
     }
+    const double rt = 1.0 / sqrt(P.cmu[iq] * P.cwt[iq]);
+    const double s = rt * X[iq * nn + jq], d = -rt * Z[iq * nn + jq] / k;
+    const double up = 0.5 * (s + d), dn = 0.5 * (s - d);
+    gc[(iq + nn) * N + jq + nn] = up;
+    gc[(nn - 1 - iq) * N + jq + nn] = dn;
+    gc[(iq + nn) * N + nn - 1 - jq] = dn;
+    gc[(nn - 1 - iq) * N + nn - 1 - jq] = up;
   }
   // full scattering kernel in CMU order (first nn = +mu, then -mu): C(mu_i, mu_j)
-  for (int iq = 0; iq < nn; ++iq) {
-    for (int jq = 0; jq < nn; ++jq) {
-      double sp = 0.0, sm = 0.0, sg = 1.0;
-      for (int l = mazim; l < N; ++l) {
-        const double v = gl[l] * ylmc[l * N + iq] * ylmc[l * N + jq];
-        sp += v;
-        sm += sg * v;
-        sg = -sg;
-      }
-      const double cp = 0.5 * sp * P.cwt[jq], cm = 0.5 * sm * P.cwt[jq];
-      cc[iq * N + jq] = cp; cc[iq * N + jq + nn] = cm;
-      cc[(iq + nn) * N + jq] = cm; cc[(iq + nn) * N + jq + nn] = cp;
+  LFOR(idx, nn * nn) {
+    const int iq = idx / nn, jq = idx - iq * nn;
+    double sp = 0.0, sm = 0.0, sg = 1.0;
+    for (int l = mazim; l < N; ++l) {
+      const double v = gl[l] * ylmc[l * N + iq] * ylmc[l * N + jq];
+      sp += v;
+      sm += sg * v;
+      sg = -sg;
     }
+    const double cp = 0.5 * sp * P.cwt[jq], cm = 0.5 * sm * P.cwt[jq];
+    cc[iq * N + jq] = cp; cc[iq * N + jq + nn] = cm;
+    cc[(iq + nn) * N + jq] = cm; cc[(iq + nn) * N + jq + nn] = cp;
   }
+  LSYNC();
   auto cmu_of = [&](int iq) { return iq < nn ? P.cmu[iq] : -P.cmu[iq - nn]; };
   auto ylmc_of = [&](int l, int iq) {
     return iq < nn ? ylmc[l * N + iq] : (((l - mazim) & 1) ? -ylmc[l * N + iq - nn] : ylmc[l * N + iq - nn]);
   };
   if (fbeam > 0.0) {  // c_upbeam
     double* zz = w + M.zz + (long)lc * N;
-    for (int iq = 0; iq < N; ++iq) {
+    LFOR(iq, N) {
       for (int jq = 0; jq < N; ++jq) arr[iq * N + jq] = -cc[iq * N + jq];
       arr[iq * N + iq] += 1.0 + cmu_of(iq) / umu0;
       double sum = 0.0;
       for (int l = mazim; l < N; ++l) sum += gl[l] * ylmc_of(l, iq) * ylm0[l];
       zj[iq] = (2.0 - delm0) * fbeam * sum / (4.0 * kPi);
     }
-    if (!lu_factor(arr, N, ipvt) && st == ST_OK) st = ST_SINGULAR;
-    lu_solve(arr, N, ipvt, zj);
-    for (int iq = 0; iq < nn; ++iq) { zz[iq + nn] = zj[iq]; zz[nn - 1 - iq] = zj[iq + nn]; }
+    LSYNC();
+    if (ltid == 0) {
+      if (!lu_factor(arr, N, ipvt) && st == ST_OK) st = ST_SINGULAR;
+      lu_solve(arr, N, ipvt, zj);
+      for (int iq = 0; iq < nn; ++iq) { zz[iq + nn] = zj[iq]; zz[nn - 1 - iq] = zj[iq + nn]; }
+    }
+    LSYNC();
   }
   if (planck && mazim == 0) {  // c_upisot
     double* zp0 = w + M.zp0 + (long)lc * N;
     double* zp1 = w + M.zp1 + (long)lc * N;
     const double oprim = w[M.oprim + lc], xr0 = w[M.xr0 + lc], xr1 = w[M.xr1 + lc];
-    for (int iq = 0; iq < N; ++iq) {
+    LFOR(iq, N) {
       for (int jq = 0; jq < N; ++jq) arr[iq * N + jq] = -cc[iq * N + jq];
       arr[iq * N + iq] += 1.0;
       z1[iq] = (1.0 - oprim) * xr1;
     }
-    if (!lu_factor(arr, N, ipvt) && st == ST_OK) st = ST_SINGULAR;
-    lu_solve(arr, N, ipvt, z1);
-    for (int iq = 0; iq < N; ++iq) z0[iq] = (1.0 - oprim) * xr0 + cmu_of(iq) * z1[iq];
-    lu_solve(arr, N, ipvt, z0);
-    for (int iq = 0; iq < nn; ++iq) {
-      zp0[iq + nn] = z0[iq]; zp1[iq + nn] = z1[iq];
-      zp0[nn - 1 - iq] = z0[iq + nn]; zp1[nn - 1 - iq] = z1[iq + nn];
+    LSYNC();
+    if (ltid == 0) {
+      if (!lu_factor(arr, N, ipvt) && st == ST_OK) st = ST_SINGULAR;
+      lu_solve(arr, N, ipvt, z1);
+      for (int iq = 0; iq < N; ++iq) z0[iq] = (1.0 - oprim) * xr0 + cmu_of(iq) * z1[iq];
+      lu_solve(arr, N, ipvt, z0);
+      for (int iq = 0; iq < nn; ++iq) {
+        zp0[iq + nn] = z0[iq]; zp1[iq + nn] = z1[iq];
+        zp0[nn - 1 - iq] = z0[iq + nn]; zp1[nn - 1 - iq] = z1[iq + nn];
+      }
     }
+    LSYNC();
   }
   if (user_angles) {  // c_terpev + c_terpso
     double* gu = w + M.gu + (long)lc * U * N;
@@ -338,7 +379,7 @@ B200_FN_ATTR inline int intensity_layer(const IntensityParams& P, const Intensit
     auto yrow = [&](int l, int r) {
       return r < nn ? (((l - mazim) & 1) ? -ylmc[l * N + nn - 1 - r] : ylmc[l * N + nn - 1 - r]) : ylmc[l * N + r - nn];
     };
-    for (int jq = 0; jq < N; ++jq) {
+    LFOR(jq, N) {  // (eigenvectors are independent: wk is this thread's own)
       for (int l = mazim; l < N; ++l) {
         double sum = 0.0;
         for (int r = 0; r < N; ++r) sum += wrow(r) * yrow(l, r) * gc[r * N + jq];
@@ -350,25 +391,29 @@ B200_FN_ATTR inline int intensity_layer(const IntensityParams& P, const Intensit
         gu[iu * N + jq] = sum;
       }
     }
+    LSYNC();  // (thread 0's own vectors ARE the shared ones)
     if (fbeam > 0.0) {
       const double* zz = w + M.zz + (long)lc * N;
       const double fact = (2.0 - delm0) * fbeam / (4.0 * kPi);
-      for (int l = mazim; l < N; ++l) {
+      LFOR(l, N) {
+        if (l < mazim) continue;
         double ps = 0.0;
         for (int r = 0; r < N; ++r) ps += wrow(r) * yrow(l, r) * zz[r];
-        wk[l] = 0.5 * gl[l] * ps;
+        wks[l] = 0.5 * gl[l] * ps;
       }
-      for (int iu = 0; iu < U; ++iu) {
+      LSYNC();
+      LFOR(iu, U) {
         double sum = 0.0;
-        for (int l = mazim; l < N; ++l) sum += ylmu[l * U + iu] * (wk[l] + fact * gl[l] * ylm0[l]);
+        for (int l = mazim; l < N; ++l) sum += ylmu[l * U + iu] * (wks[l] + fact * gl[l] * ylm0[l]);
         w[M.zbeam + (long)lc * U + iu] = sum;
       }
+      LSYNC();
     }
     if (planck && mazim == 0) {
       const double* zp0 = w + M.zp0 + (long)lc * N;
       const double* zp1 = w + M.zp1 + (long)lc * N;
-      double* psi0 = wk; double* psi1 = wk + N;
-      for (int l = 0; l < N; ++l) {
+      double* psi0 = wks; double* psi1 = wks + N;
+      LFOR(l, N) {
         double p0 = 0.0, p1 = 0.0;
         for (int r = 0; r < N; ++r) {
           const double c = wrow(r) * yrow(l, r);
@@ -378,8 +423,9 @@ B200_FN_ATTR inline int intensity_layer(const IntensityParams& P, const Intensit
         psi0[l] = 0.5 * gl[l] * p0;
         psi1[l] = 0.5 * gl[l] * p1;
       }
+      LSYNC();
       const double om = 1.0 - w[M.oprim + lc];
-      for (int iu = 0; iu < U; ++iu) {
+      LFOR(iu, U) {
         double s0 = 0.0, s1 = 0.0;
         for (int l = 0; l < N; ++l) { s0 += ylmu[l * U + iu] * psi0[l]; s1 += ylmu[l * U + iu] * psi1[l]; }
         w[M.z0u + (long)lc * U + iu] = s0 + om * w[M.xr0 + lc];
@@ -387,8 +433,11 @@ B200_FN_ATTR inline int intensity_layer(const IntensityParams& P, const Intensit
       }
     }
   }
+  LSYNC();  // (COOP: the next layer re-uses the shared matrices)
   return st;
 }
+#undef LFOR
+#undef LSYNC
 
 // c_xi_func / c_single_scat / c_secondary_scat (Nakajima-Tanaka TMS/IMS)
 B200_FN_ATTR inline double nt_xifunc(double u1, double u2, double u3, double tau) {
@@ -586,9 +635,16 @@ B200_FN_ATTR inline void solve_intensity_one(const IntensityParams& P, long s, d
     // ---- per-layer eigen / particular solutions: layers are independent ----
     {
       int lst = ST_OK;
-      B200_PAR_FOR(lc, ncut) {
-        const int r = intensity_layer(P, M, w, scr, lc, mazim, planck, user_angles, fbeam, umu0);
-        if (r != ST_OK && lst == ST_OK) lst = r;
+      if (ncut <= kCoopMaxLayers) {  // few layers: the CTA works on one layer at a time (see intensity_layer)
+        for (int lc = 0; lc < ncut; ++lc) {
+          const int r = intensity_layer<true>(P, M, w, w + M.thread_scratch, scr, lc, mazim, planck, user_angles, fbeam, umu0, tid, nthr);
+          if (r != ST_OK && lst == ST_OK) lst = r;
+        }
+      } else {
+        B200_PAR_FOR(lc, ncut) {
+          const int r = intensity_layer<false>(P, M, w, scr, scr, lc, mazim, planck, user_angles, fbeam, umu0, 0, 1);
+          if (r != ST_OK && lst == ST_OK) lst = r;
+        }
       }
       w[M.red + tid] = (double)lst;
     }
