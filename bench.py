@@ -616,8 +616,45 @@ def bench_band(ctx, args, nwave, ncol, nlyr, steps, warmup, hbm_peak, hbm_src):
                            "clocks": r["clocks"]})
             del r, wl
             torch.cuda.empty_cache()
+        # BASELINE config 2 once more, as a radiation BAND (aerosol optics on the GPU -> mixing -> solve -> band sum in one call)
+        if not args.no_e2e:
+            others[0]["band_level"] = sw_band_bench(ctx, 10)
         out["other_workloads"] = others
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 2 at the band level: what examples/amars_sw.cpp does by hand (S8 + H2SO4 attenuators, mixing, disort,
+# integrate_result) as ONE call, inputs resident in HBM and end to end with host tensors
+# ---------------------------------------------------------------------------------------------
+def sw_band_bench(ctx, steps):
+    import torch
+    from pyharp_b200 import sw_band
+    nwave, ncol, nlyr = DEFAULT_NWAVE["amars_sw"], DEFAULT_COLS["amars_sw"], DEFAULT_NLYR["amars_sw"]
+    band, inp = sw_band.make(nwave, ncol, nlyr)
+    t = lambda a: torch.from_numpy(a).to(ctx.dev)
+    d = dict(conc=t(inp["conc"]), dz=t(inp["dz"]), bc={k: t(v) for k, v in inp["bc"].items()})
+    for _ in range(3):
+        bflx = band.forward_band(d["conc"], d["dz"], d["bc"], {})
+    assert bool(torch.isfinite(bflx).all())
+    ms, ms_max = timed_region(ctx, lambda: band.forward_band(d["conc"], d["dz"], d["bc"], {}, check=False), steps)
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    h = dict(conc=pin(inp["conc"]), dz=pin(inp["dz"]), bc={k: pin(v) for k, v in inp["bc"].items()})
+    for _ in range(2):
+        out_h = band.forward_band(h["conc"], h["dz"], h["bc"], {})
+    assert float((out_h - bflx.cpu()).abs().max() / bflx.abs().max()) < 1e-12
+    dt = wall_region(ctx, lambda: band.forward_band(h["conc"], h["dz"], h["bc"], {}), steps)
+    nsolve = nwave * ncol
+    return {"workload": f"amars_sw as a band: {nwave} wavenumbers x {ncol} columns x {nlyr} layers, S8 + H2SO4 aerosol attenuators, nstr=8, beam",
+            "note": "a synthetic haze on the reference's own S8 / H2SO4 tables (pyharp_b200/sw_band.py): strongly absorbing wavenumbers reach "
+                    "the absorption cut-off part of the way down, so a solve is cheaper here than in the solver-level amars_sw line above -- "
+                    "compare e2e with value, not with that line",
+            "value": nsolve * steps / (ms_max * 1e-3), "unit": "solves/s", "ms_per_step": ms_max / steps,
+            "e2e": {"value": nsolve * steps / dt, "unit": "solves/s", "ms_per_step": 1e3 * dt / steps,
+                    "h2d_bytes_per_step": int(inp["conc"].nbytes + inp["dz"].nbytes + sum(v.nbytes for v in inp["bc"].values())),
+                    "d2h_bytes_per_step": int(out_h.nbytes),
+                    "api": "pyharp_b200.RadiationBand.forward_band(host tensors) -> b200_band_forward_host: conc and (nwave, ncol) "
+                           "boundary fields in, band flux (ncol, nlyr+1, 2) out"}}
 
 
 # ---------------------------------------------------------------------------------------------
