@@ -20,8 +20,13 @@ def timeit(fn, n):
 
 
 dev = torch.device("cuda", 0)
-for name, nlyr in (("amars_sw", 40), ("amars_lw", 80)):
-    for nwave in (32, 128, 500, 1184, 2368, 4736, 9472, 18944, 37888):
+import os
+CASES = [("amars_sw", 40, (32, 128, 500, 1184, 2368, 4736, 9472, 18944, 37888)), ("amars_lw", 80, (32, 128, 500, 1184, 2368, 4736, 9472, 18944, 37888)),
+         ("lbl", 40, (1184, 4736, 12500, 25000, 50000, 100000))]
+if os.environ.get("CASES"):
+    CASES = [c for c in CASES if c[0] in os.environ["CASES"].split(",")]
+for name, nlyr, sizes in CASES:
+    for nwave in sizes:
         wl = W.make(name, nwave=nwave, ncol=1, nlyr=nlyr)
         t = lambda a: None if a is None else torch.from_numpy(a).to(dev)
         dp, dbc, dt_ = t(wl.prop), {k: t(v) for k, v in wl.bc.items()}, t(wl.temf)
@@ -29,4 +34,7 @@ for name, nlyr in (("amars_sw", 40), ("amars_lw", 80)):
         for form, (warp, split) in (("fused", (0, 0)), ("warp", (1 << 30, 0)), ("split", (0, 1))):
             ds = Disort(wl.options()).set_warp_solve_max(warp).set_layer_split(split)
             row[form + "_ms"] = round(timeit(lambda: ds.forward(dp, dbc, dt_), 30), 4)
+            if name == "lbl":  # the spectral-point sharding's step: solve + fused band integration (one column: warp-reduced form)
+                w = torch.ones(nwave, dtype=torch.float64, device=dev)
+                row[form + "_band_ms"] = round(timeit(lambda: ds.forward_band(dp, dbc, dt_, w, check=False), 30), 4)
         print(json.dumps(row), flush=True)

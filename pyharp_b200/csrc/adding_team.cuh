@@ -376,6 +376,9 @@ __device__ __forceinline__ void team_adding_sweep(const SolveParams& p, const QT
 
   // ---- bottom boundary (Lambertian surface), as in solve_flux_one
   double* out = (BAND != kBandOff) ? p.bflx_t + cm.j : p.flx + s * (nlyr + 1) * 2;
+  // (batches of fewer than 32 columns: the host keeps p.nrep replicas of the band-flux buffer so that the reductions of the
+  // many spectral points of one column do not serialise on the same L2 addresses; CTA b adds into replica b % nrep)
+  if (BAND != kBandOff && p.nrep > 1) out += (long)(blockIdx.x % (unsigned)p.nrep) * p.rep_stride;
   const double wg = (BAND != kBandOff) ? p.weights[cm.n] : 1.0;
   const long ostr = p.ncol;
   constexpr int EB = (BAND != kBandOff) ? kBandAtomic : kBandOff;

@@ -309,7 +309,9 @@ static int ring_end(b200disort_handle* h, cudaStream_t stream) {
 // Layer-split form by default (measured, profiles/r02/sweeps.md e36, e45): from nstr = 16 up (nstr = 12 loses 14 %, nstr = 16 /
 // 24 / 32 gain 1.3-1.9x / 1.3x / 2x), and at nstr = 8 for batches above the warp-per-solve form's range of at most this many
 // solves (1184 < n <= 8192: 0.14-0.21 ms per call against 0.23 ms for the fused kernel)
-static const long kSplitSmallMax = 8192;
+// (nstr = 4: the split form is instantiated and tested, but never faster than the fused kernel -- a call of 10^3..10^5 solves is
+// bound by its ~0.1 ms of launch / host overhead, sweeps e46 -- so it is off by default there)
+static long small_max(int nn) { return nn == 4 ? 8192 : 0; }
 
 // Launch the flux kernel for p.nlocal solves on `stream` with the given back-sweep workspace.
 // timed = record the launch in the handle's event ring (handle stream only).
@@ -332,8 +334,8 @@ int b200::launch_flux(b200disort_handle* h, SolveParams& p, cudaStream_t stream,
     // call -- and from ~10^4 solves on the fused kernel is; in between the split form is 1.1-1.5x faster than either)
     static const long env_warp = std::getenv("B200DISORT_WARP_SOLVE_MAX") ? std::atol(std::getenv("B200DISORT_WARP_SOLVE_MAX")) : -1;
     const long warp_max = h->warp_solve_max >= 0 ? h->warp_solve_max : env_warp >= 0 ? env_warp : (long)h->sm_count * 8;
-    const bool use = mode == 1 || (mode < 0 && (inst->nn >= 8 || (inst->nn == 4 && p.nlocal > warp_max &&
-                                                                  p.nlocal <= (env_small >= 0 ? env_small : kSplitSmallMax))));
+    const bool use = mode == 1 || (mode < 0 && (inst->nn >= 8 || (p.nlocal > warp_max &&
+                                                                  p.nlocal <= (env_small >= 0 ? env_small : small_max(inst->nn)))));
     if (use) {
       long chunk = env_chunk > 0 ? env_chunk : (long)h->sm_count * 256 * 2;
       chunk = std::min<long>(chunk, p.nlocal);

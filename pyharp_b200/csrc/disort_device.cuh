@@ -619,9 +619,9 @@ B200_HD int layer_ops_any(const SolveParams& p, const QT& qt, const SolveCommon<
 }
 template <int NN, int BAND, typename QT>
 B200_HD void adding_sweep_any(const SolveParams& p, const QT& qt, const SolveCommon<NN>& cm, long s, const double* pr, int ncut,
-                              bool lyrcut, int st, const double* opsbuf, double* recbuf, long bstr, long blane) {
-  if constexpr (NN <= B200_UNROLL_MAX_NN) adding_sweep_u<NN, BAND>(p, qt, cm, s, pr, ncut, lyrcut, st, opsbuf, recbuf, bstr, blane);
-  else adding_sweep_r<NN, BAND>(p, qt, cm, s, pr, ncut, lyrcut, st, opsbuf, recbuf, bstr, blane);
+                              bool lyrcut, int st, const double* opsbuf, double* recbuf, long bstr, long blane, bool active) {
+  if constexpr (NN <= B200_UNROLL_MAX_NN) adding_sweep_u<NN, BAND>(p, qt, cm, s, pr, ncut, lyrcut, st, opsbuf, recbuf, bstr, blane, active);
+  else adding_sweep_r<NN, BAND>(p, qt, cm, s, pr, ncut, lyrcut, st, opsbuf, recbuf, bstr, blane, active);
 }
 
 // finishes a pending (carried) back sweep after a thread's last solve

@@ -198,13 +198,13 @@ cudaError_t launch_warp(const SolveParams& p, unsigned grid, int block, cudaStre
 // traffic per layer and solve -- less than the spill traffic it removes -- and the layer phase has nlyr times the
 // parallelism of the batch, so small batches fill the GPU as well.
 // ---------------------------------------------------------------------------
-#if B200_NN >= 6 || B200_NN == 4
+#if B200_NN >= 6 || B200_NN == 4 || B200_NN == 2
 #define B200_HAVE_SPLIT 1
 #else
 #define B200_HAVE_SPLIT 0
 #endif
 // thread form of the adding phase (the team form replaces it where it exists; kept at nstr >= 12 for comparison)
-#define B200_HAVE_SPLIT_THREAD (B200_NN >= 6)
+#define B200_HAVE_SPLIT_THREAD (B200_NN >= 6 || B200_NN == 2)
 #if B200_HAVE_SPLIT
 // Legendre polynomials at the beam angle: 1 = read from the prefix pass's buffer where they are used, 0 = recomputed per item
 #ifndef B200_SPLIT_Y0BUF
@@ -320,8 +320,10 @@ template <int BAND>
 __global__ void __launch_bounds__(128, B200_SPLIT_MINB_B) split_adding_kernel(SolveParams p, long c0, long cn, const int* cutv,
                                                                                const int* stl, const double* ops, double* rec) {
   constexpr int NN = B200_NN, NOPS = kOpsDoubles<NN>;
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= cn) return;
+  const long ii = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = ii < cn;
+  if (BAND != kBandWarpRed && !active) return;  // (warp-reduced band integration: every lane of the warp stays)
+  const long i = active ? ii : cn - 1;
   const long s = c0 + i;
   const int nlyr = p.nlyr;
   SolveCommon<NN> cm;
@@ -331,9 +333,8 @@ __global__ void __launch_bounds__(128, B200_SPLIT_MINB_B) split_adding_kernel(So
   const int st = status_merge_u(cm.st, sl == kSplitNoStatus ? (int)ST_OK : sl);
   const long blk = i / kWsLanes, lane = i % kWsLanes;
   adding_sweep_any<NN, BAND>(p, c_qt, cm, s, pr, cv & 0xffff, (cv >> 16) != 0, st, ops + blk * ((long)nlyr * NOPS * kWsLanes) + lane,
-                             rec + blk * ((long)nlyr * kNsave * kWsLanes) + lane, kWsLanes, lane);
+                             rec + blk * ((long)nlyr * kNsave * kWsLanes) + lane, kWsLanes, lane, active);
 }
-
 #endif
 #if B200_HAVE_TEAM
 template <int BAND>
@@ -414,6 +415,12 @@ cudaError_t launch_split(const SolveParams& p, long chunk, int sm_count, cudaStr
     }
 #endif
 #if B200_HAVE_SPLIT_THREAD
+#if B200_HAVE_WARPRED
+    if (band && p.warp_red > 0) {  // fewer than 32 columns: warp-reduced band integration (emit_flux, BAND = 2)
+      split_adding_kernel<2><<<gs, 128, 0, stream>>>(p, c0, cn, cutv, stl, ops, rec);
+      continue;
+    }
+#endif
     if (band) split_adding_kernel<1><<<gs, 128, 0, stream>>>(p, c0, cn, cutv, stl, ops, rec);
     else split_adding_kernel<0><<<gs, 128, 0, stream>>>(p, c0, cn, cutv, stl, ops, rec);
 #endif

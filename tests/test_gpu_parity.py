@@ -30,8 +30,8 @@ FORMS = ["thread_per_solve", "warp_per_solve", "layer_split"]
 def _skip_form(form, nstr):
     if form == "warp_per_solve" and nstr > 8:
         pytest.skip("the warp-per-solve form is instantiated for nstr <= 8")
-    if form == "layer_split" and nstr not in (8, 12, 16, 24, 32):
-        pytest.skip("the layer-split form is instantiated for nstr = 8 and nstr >= 12")
+    if form == "layer_split" and nstr not in (4, 8, 12, 16, 24, 32):
+        pytest.skip("the layer-split form is instantiated for nstr = 4, 8 and nstr >= 12")
 
 
 def _with_form(ds, form):
@@ -152,7 +152,7 @@ def test_every_stream_count(cuda_device, nstr, thermal):
     t = lambda a: None if a is None else torch.from_numpy(a).to(cuda_device)
     # the fused kernel, then (where they exist) the warp-per-solve / layer-split forms
     for form in ("thread_per_solve", "warp_per_solve", "layer_split"):
-        if (form == "layer_split" and nstr not in (8, 12, 16, 24, 32)) or (form == "warp_per_solve" and nstr > 8):
+        if (form == "layer_split" and nstr not in (4, 8, 12, 16, 24, 32)) or (form == "warp_per_solve" and nstr > 8):
             continue
         ds = _with_form(Disort(wl.options()), form)
         flx = ds.forward(t(prop), {k: t(v) for k, v in bc.items()}, t(temf)).cpu().numpy()
@@ -160,7 +160,7 @@ def test_every_stream_count(cuda_device, nstr, thermal):
         assert G.diverr(flx, ref) < RTOL
 
 
-@pytest.mark.parametrize("nstr", [8, 12, 16])
+@pytest.mark.parametrize("nstr", [4, 8, 12, 16])
 def test_layer_split_matches_fused_kernel(cuda_device, nstr):
     """nstr >= 12: the layer-split form against the fused kernel on a batch with absorption cut-offs at different
     levels, zero-thickness layers and a rejected input: same status words,
