@@ -389,6 +389,30 @@ __global__ void band_finish_kernel(const double* __restrict__ acc, int rows, int
   }
 }
 
+// the same for the replicated buffer of the warp-reduced form (fewer than 32 columns, nrep = 64 replicas): one WARP per
+// output element, lanes over the replicas, shuffle tree.  The tile kernel above walked the replicas serially in a handful
+// of threads -- 64 dependent L2 round trips, ~50 us of a 135 us line-by-line call (profiles/r02/sweeps.md, e47)
+__global__ void band_finish_rep_kernel(const double* __restrict__ acc, int rows, int ncol, int nrep, double* __restrict__ bflx) {
+  const int lane = threadIdx.x & 31;
+  const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= (long)rows * ncol) return;
+  const int r = (int)(wid / ncol), c = (int)(wid - (long)r * ncol);
+  double v = 0.0;
+  for (int k = lane; k < nrep; k += 32) v += acc[((long)k * rows + r) * ncol + c];
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) bflx[(long)c * rows + r] = v;
+}
+
+static void launch_band_finish(const double* acc, int rows, int ncol, int nrep, double* bflx, cudaStream_t st) {
+  if (nrep > 1) {
+    const long warps = (long)rows * ncol;
+    band_finish_rep_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(acc, rows, ncol, nrep, bflx);
+  } else {
+    band_finish_kernel<<<dim3((unsigned)((ncol + 31) / 32), (unsigned)((rows + 31) / 32)), dim3(32, 8), 0, st>>>(acc, rows, ncol, nrep, bflx);
+  }
+}
+
 // heating rate from the band flux, examples/amars_sw.cpp:290-301 (same evaluation order); dz per layer
 __global__ void band_heating_kernel(const double* __restrict__ bflx, const double* __restrict__ rho,
                                     const double* __restrict__ dz, double cp, long ncol, int nlyr, double* __restrict__ out) {
@@ -609,7 +633,7 @@ int run_chunk(b200_band* b, cudaStream_t st, const Chunk& c, const double* d_dz,
     CU_TRY(cudaMemsetAsync(c.acc, 0, (size_t)p.nrep * rows * cc * sizeof(double), st));
     int rc = launch_flux(h, p, st, ws, ws_bytes, true);
     if (rc != B200DISORT_OK) return rc;
-    band_finish_kernel<<<dim3((unsigned)((cc + 31) / 32), (unsigned)((rows + 31) / 32)), dim3(32, 8), 0, st>>>(c.acc, rows, cc, p.nrep, c.bflx);
+    launch_band_finish(c.acc, rows, cc, p.nrep, c.bflx, st);
     CU_TRY(cudaGetLastError());
     h->stats.kernel_launches += 1;
   }
@@ -1086,8 +1110,7 @@ extern "C" int b200disort_solve_band(b200disort_handle* h, const double* prop, i
   p.rep_stride = (long)rows * c.ncol;
   rc = launch_flux(h, p, st, &h->d_ws, &h->ws_bytes, true);
   if (rc != B200DISORT_OK) return rc;
-  band_finish_kernel<<<dim3((unsigned)((c.ncol + 31) / 32), (unsigned)((rows + 31) / 32)), dim3(32, 8), 0, st>>>(h->d_acc, rows,
-                                                                                                               c.ncol, p.nrep, bflx);
+  launch_band_finish(h->d_acc, rows, c.ncol, p.nrep, bflx, st);
   CU_TRY(cudaGetLastError());
   h->stats.kernel_launches += 1;
   return B200DISORT_OK;
