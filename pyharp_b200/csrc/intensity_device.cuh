@@ -144,6 +144,38 @@ B200_FN_ATTR inline bool lu_factor(double* a, int n, int* ipvt) {
   return ok;
 }
 
+// the same factorisation with the row updates below the pivot spread over the CTA (COOP; every thread must call it).
+// Thread 0 searches the pivot and swaps the rows, a barrier publishes them, the rows r > k are updated by different
+// threads, a second barrier closes the step.  !COOP: the statements of lu_factor on one thread.
+template <bool COOP>
+B200_FN_ATTR inline bool lu_factor_team(double* a, int n, int* ipvt, int ltid, int lnthr) {
+  bool ok = true;
+  for (int k = 0; k < n; ++k) {
+    if (ltid == 0) {
+      int p = k;
+      double amax = fabs(a[k * n + k]);
+      for (int r = k + 1; r < n; ++r)
+        if (fabs(a[r * n + k]) > amax) { amax = fabs(a[r * n + k]); p = r; }
+      ipvt[k] = p;
+      if (amax != 0.0 && p != k)
+        for (int c = k; c < n; ++c) {
+          double t = a[k * n + c]; a[k * n + c] = a[p * n + c]; a[p * n + c] = t;
+        }
+    }
+    if (COOP) { B200_SYNC(); }
+    const double piv = a[k * n + k];
+    if (piv == 0.0) { ok = false; if (COOP) { B200_SYNC(); } continue; }  // (the whole column below the diagonal is zero)
+    const double rp = 1.0 / piv;
+    for (int r = k + 1 + ltid; r < n; r += lnthr) {
+      const double f = a[r * n + k] * rp;
+      a[r * n + k] = f;
+      for (int c = k + 1; c < n; ++c) a[r * n + c] -= f * a[k * n + c];
+    }
+    if (COOP) { B200_SYNC(); }
+  }
+  return ok;
+}
+
 B200_FN_ATTR inline void lu_solve(const double* a, int n, const int* ipvt, double* b) {
   for (int k = 0; k < n; ++k) {
     const int p = ipvt[k];
@@ -196,6 +228,51 @@ B200_FN_ATTR inline bool jacobi_dyn(double* g, double* y, int n) {
   return false;
 }
 
+// the same iteration with each rotation's row / column updates spread over the CTA (COOP; every thread must call it): all
+// threads read the 2 x 2 block and form the rotation redundantly, a barrier, the updates of the n rows by different
+// threads (thread 0 the 2 x 2 block itself), a barrier.  Same statements per element as jacobi_dyn.
+template <bool COOP>
+B200_FN_ATTR inline bool jacobi_team(double* g, double* y, int n, int ltid, int lnthr) {
+  const double eps2 = 1.0e-31;
+  for (int idx = ltid; idx < n * n; idx += lnthr) y[idx] = (idx / n == idx % n) ? 1.0 : 0.0;
+  if (COOP) { B200_SYNC(); }
+  for (int sweep = 0; sweep <= 30; ++sweep) {
+    bool conv = true;
+    for (int p = 0; p < n - 1 && conv; ++p)
+      for (int q = p + 1; q < n; ++q)
+        if (g[q * n + p] * g[q * n + p] > eps2 * fabs(g[p * n + p] * g[q * n + q])) { conv = false; break; }
+    if (conv) return true;
+    for (int p = 0; p < n - 1; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const double gpq = g[q * n + p], gpp = g[p * n + p], gqq = g[q * n + q];
+        if (!(gpq * gpq > eps2 * fabs(gpp * gqq))) continue;  // (uniform: every thread reads the same values)
+        const double d = gqq - gpp, b2 = 2.0 * gpq;
+        const double r = sqrt(d * d + b2 * b2);
+        const double t = b2 / (d + copysign(r, d));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c, tau = s / (1.0 + c);
+        if (COOP) { B200_SYNC(); }  // everybody has read the block
+        if (ltid == 0) {
+          g[p * n + p] = gpp - t * gpq;
+          g[q * n + q] = gqq + t * gpq;
+          g[q * n + p] = g[p * n + q] = 0.0;
+        }
+        for (int r2 = ltid; r2 < n; r2 += lnthr) {
+          if (r2 != p && r2 != q) {
+            const double a = g[r2 * n + p], b = g[r2 * n + q];
+            const double na = a - s * (b + tau * a), nb = b + s * (a - tau * b);
+            g[r2 * n + p] = g[p * n + r2] = na;
+            g[r2 * n + q] = g[q * n + r2] = nb;
+          }
+          const double a = y[r2 * n + p], b = y[r2 * n + q];
+          y[r2 * n + p] = a - s * (b + tau * a);
+          y[r2 * n + q] = b + s * (a - tau * b);
+        }
+        if (COOP) { B200_SYNC(); }
+      }
+  }
+  return false;
+}
+
 // ------------------------------------------------------------------------------------------
 // One layer, one azimuth mode: eigen-solution (c_sol_eigen), beam (c_upbeam) and thermal
 // (c_upisot) particular solutions, interpolation to user angles (c_terpev / c_terpso).
@@ -206,9 +283,9 @@ B200_FN_ATTR inline bool jacobi_dyn(double* g, double* y, int n) {
 //   COOP = false  one thread owns the layer (the CTA's threads take different layers): ltid = 0, lnthr = 1, no barriers;
 //   COOP = true   the whole CTA works on ONE layer -- for columns with fewer layers than threads (tests/test_disort.cpp
 //                 has a single layer: its per-layer phase ran on one thread while 63 waited, 2.1 ms per 10-solve call).
-//                 Loops over independent outputs are spread over the CTA (LFOR), the short factorisations (Cholesky
-//                 8 x 8, Jacobi, the 16 x 16 pivoted LU of c_upbeam / c_upisot) stay on one thread, CTA barriers separate
-//                 the phases.  `scr` holds the layer's matrices (shared by the CTA when COOP), `prv` this thread's own
+//                 Loops over independent outputs are spread over the CTA (LFOR) -- including the row updates of the
+//                 pivoted LU of c_upbeam / c_upisot and of every Jacobi rotation --, the 8 x 8 Cholesky and the
+//                 triangular solves stay on one thread, CTA barriers separate the phases.  `scr` holds the layer's matrices (shared by the CTA when COOP), `prv` this thread's own
 //                 vectors.  Every thread must call it with the same arguments.
 #define LFOR(i, n) for (int i = ltid; i < (n); i += lnthr)
 #define LSYNC() do { if (COOP) { B200_SYNC(); } } while (0)
@@ -279,9 +356,7 @@ B200_FN_ATTR inline int intensity_layer(const IntensityParams& P, const Intensit
     G[i * nn + c] = G[c * nn + i] = v;
   }
   LSYNC();
-  if (ltid == 0) {
-    if (!jacobi_dyn(G, Y, nn) && st == ST_OK) st = ST_EIGEN_FAIL;
-  }
+  if (!jacobi_team<COOP>(G, Y, nn, ltid, lnthr) && st == ST_OK) st = ST_EIGEN_FAIL;
   LSYNC();
   // X = L^-T Y, Z = L Y (columns = eigenmodes); s = T^-1 X, d = -T^-1 Z / k with T = sqrt(mu w)
   LFOR(c, nn) {
@@ -343,8 +418,8 @@ B200_FN_ATTR inline int intensity_layer(const IntensityParams& P, const Intensit
       zj[iq] = (2.0 - delm0) * fbeam * sum / (4.0 * kPi);
     }
     LSYNC();
+    if (!lu_factor_team<COOP>(arr, N, ipvt, ltid, lnthr) && st == ST_OK) st = ST_SINGULAR;
     if (ltid == 0) {
-      if (!lu_factor(arr, N, ipvt) && st == ST_OK) st = ST_SINGULAR;
       lu_solve(arr, N, ipvt, zj);
       for (int iq = 0; iq < nn; ++iq) { zz[iq + nn] = zj[iq]; zz[nn - 1 - iq] = zj[iq + nn]; }
     }
@@ -360,8 +435,8 @@ B200_FN_ATTR inline int intensity_layer(const IntensityParams& P, const Intensit
       z1[iq] = (1.0 - oprim) * xr1;
     }
     LSYNC();
+    if (!lu_factor_team<COOP>(arr, N, ipvt, ltid, lnthr) && st == ST_OK) st = ST_SINGULAR;
     if (ltid == 0) {
-      if (!lu_factor(arr, N, ipvt) && st == ST_OK) st = ST_SINGULAR;
       lu_solve(arr, N, ipvt, z1);
       for (int iq = 0; iq < N; ++iq) z0[iq] = (1.0 - oprim) * xr0 + cmu_of(iq) * z1[iq];
       lu_solve(arr, N, ipvt, z0);
