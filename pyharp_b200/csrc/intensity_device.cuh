@@ -58,11 +58,20 @@ struct IntensityParams {
   long s0, nlocal;
 };
 
+// columns of at most this many layers run the per-layer phase CTA-cooperatively (one layer at a time) instead of one
+// thread per layer
+#ifndef B200_K3_COOP_MAX_LAYERS
+#define B200_K3_COOP_MAX_LAYERS 16
+#endif
+constexpr int kCoopMaxLayers = B200_K3_COOP_MAX_LAYERS;
+
 // ---- workspace map (offsets in doubles) -------------------------------------------------
 struct IntensityWs {
   long hdr, tauc, taucpr, dtaucp, oprim, flyr, ssa, gl, expbea, utau, utaupr, layru, pkag, xr0, xr1;
   long ylmc, ylm0, ylmu, umu, gc, kk, ll, zz, zp0, zp1, gu, zbeam, z0u, z1u, cband, b, uum, red, flux5;
   long thread_scratch, per_thread, total;
+  long shared_scr;  // (coop) the layer matrices of the cooperative per-layer phase
+  int coop;
 };
 
 B200_FN_ATTR inline IntensityWs intensity_ws_map(int nlyr, int nstr, int ntau, int numu, int nthr) {
@@ -83,18 +92,23 @@ B200_FN_ATTR inline IntensityWs intensity_ws_map(int nlyr, int nstr, int ntau, i
   m.uum = take(T * (U > N ? U : N)); m.red = take(nthr); m.flux5 = take(5 * T);
   const long layer_scr = 6 * nn * nn + 2 * N * N + 8 * N + 8;
   const long corr_scr = 3 * L + 8;
-  m.per_thread = ((layer_scr > corr_scr ? layer_scr : corr_scr) + 1) & ~1L;
+  // columns of at most kCoopMaxLayers layers run the per-layer phase CTA-cooperatively: ONE set of layer matrices shared
+  // by the CTA plus 2N+2 doubles per thread, instead of a full set per thread (64 x 8 KB at nstr = 16).  (The whole
+  // workspace of a single-layer solve is then 44 KB; keeping it in shared memory instead of global memory was measured
+  // and changes nothing -- 0.715 against 0.693 ms per call: the L1 serves the re-reads, the barriers are the cost)
+  m.coop = (L <= kCoopMaxLayers) ? 1 : 0;
+  if (m.coop) {
+    m.shared_scr = take(layer_scr);
+    const long small = 2 * N + 2;
+    m.per_thread = ((small > corr_scr ? small : corr_scr) + 1) & ~1L;
+  } else {
+    m.shared_scr = 0;
+    m.per_thread = ((layer_scr > corr_scr ? layer_scr : corr_scr) + 1) & ~1L;
+  }
   m.thread_scratch = take(m.per_thread * nthr);
   m.total = o;
   return m;
 }
-
-// columns of at most this many layers run the per-layer phase CTA-cooperatively (one layer at a time) instead of one
-// thread per layer
-#ifndef B200_K3_COOP_MAX_LAYERS
-#define B200_K3_COOP_MAX_LAYERS 16
-#endif
-constexpr int kCoopMaxLayers = B200_K3_COOP_MAX_LAYERS;
 
 // header slots
 enum { H_STATUS = 0, H_NCUT, H_LYRCUT, H_NAZ, H_KCONV, H_DONE, H_TPLANK, H_BPLANK, H_SING };
@@ -304,7 +318,7 @@ B200_FN_ATTR inline int intensity_layer(const IntensityParams& P, const Intensit
   double* cc = Z + nn * nn; double* arr = cc + N * N;
   double* zj = arr + N * N; double* z0 = zj + N; double* z1 = z0 + N; double* wks = z1 + N;  // wks: 2N+2, shared
   int* ipvt = reinterpret_cast<int*>(wks + 2 * N + 2);                                       // N ints <= N doubles
-  double* wk = prv + (wks - scr);  // this thread's own 2N+2 doubles (the same storage when !COOP)
+  double* wk = COOP ? prv : wks;  // this thread's own 2N+2 doubles (COOP: its private scratch; else the same storage)
   const double delm0 = (mazim == 0) ? 1.0 : 0.0;
   int st = ST_OK;
 
@@ -466,7 +480,6 @@ B200_FN_ATTR inline int intensity_layer(const IntensityParams& P, const Intensit
         gu[iu * N + jq] = sum;
       }
     }
-    LSYNC();  // (thread 0's own vectors ARE the shared ones)
     if (fbeam > 0.0) {
       const double* zz = w + M.zz + (long)lc * N;
       const double fact = (2.0 - delm0) * fbeam / (4.0 * kPi);
@@ -661,6 +674,17 @@ B200_FN_ATTR inline void solve_intensity_one(const IntensityParams& P, long s, d
     if (fbeam == 0.0 || fabs(1.0 - umu0) < 1.0e-5 || onlyfl || (U == 1 && fabs(1.0 - um[0]) < 1.0e-5) ||
         (U == 1 && fabs(1.0 + um[0]) < 1.0e-5) || (U == 2 && fabs(1.0 + um[0]) < 1.0e-5 && fabs(1.0 - um[1]) < 1.0e-5))
       naz = 0;
+    // Azimuth modes above the highest non-zero (delta-M scaled) moment of the column contribute exactly nothing: with
+    // gl[l] = 0 for all l >= m the scattering kernel of mode m vanishes, so do its beam source and -- m > 0, Lambertian
+    // surface -- its boundary terms, and the homogeneous system has the zero solution.  cdisort walks such modes until its
+    // convergence test has passed twice (isotropic scattering, tests/test_disort.cpp: modes 0, 1, 2); the sum is the same.
+    if (naz > 0) {
+      int lmax = 0;
+      for (int lc = 0; lc < L; ++lc)
+        for (int k = 1; k < N; ++k)
+          if (w[M.gl + (long)lc * N + k] != 0.0 && k > lmax) lmax = k;
+      if (lmax < naz) naz = lmax;
+    }
     if ((P.flags & F_INTCOR) && !(P.flags & F_OLDINTCOR) && !onlyfl && fbeam > 0.0)
       for (int lc = 0; lc < L; ++lc)
         if (w[M.flyr + lc] != 0.0 && st == ST_OK) st = ST_UNSUPPORTED;  // Buras-Emde correction not on pyharp's path
@@ -710,9 +734,9 @@ B200_FN_ATTR inline void solve_intensity_one(const IntensityParams& P, long s, d
     // ---- per-layer eigen / particular solutions: layers are independent ----
     {
       int lst = ST_OK;
-      if (ncut <= kCoopMaxLayers) {  // few layers: the CTA works on one layer at a time (see intensity_layer)
+      if (M.coop) {  // few layers: the CTA works on one layer at a time (see intensity_layer)
         for (int lc = 0; lc < ncut; ++lc) {
-          const int r = intensity_layer<true>(P, M, w, w + M.thread_scratch, scr, lc, mazim, planck, user_angles, fbeam, umu0, tid, nthr);
+          const int r = intensity_layer<true>(P, M, w, w + M.shared_scr, scr, lc, mazim, planck, user_angles, fbeam, umu0, tid, nthr);
           if (r != ST_OK && lst == ST_OK) lst = r;
         }
       } else {
