@@ -123,10 +123,12 @@ int b200disort_solve_host(b200disort_handle* h, const double* prop, int nprop,
  * thread-per-solve form.  -1 restores the default (one resident wave of warps), 0 disables the warp form. */
 int b200disort_set_warp_solve_max(b200disort_handle* h, long max_solves);
 
-/* Stream counts nstr >= 12: form of the flux solve.  1 = layer-split (the layer phase -- eigenproblem, particular
- * solutions, reflection / transmission operators, cdisort's c_sol_eigen / c_upbeam / c_upisot -- as one thread per
- * (solve, layer), then the adding recursion and the back sweep -- c_set_matrix / c_solve0 / c_fluxes -- as one thread per
- * solve), 0 = one fused kernel, -1 = the default for the stream count.  No effect at nstr <= 8. */
+/* Form of the flux solve at nstr = 4, 8 and nstr >= 12.  1 = layer-split (the layer phase -- eigenproblem, particular
+ * solutions, reflection / transmission operators: cdisort's c_sol_eigen / c_upbeam / c_upisot -- as one thread per
+ * (solve, layer), then the adding recursion and the back sweep -- c_set_matrix / c_solve0 / c_fluxes -- as a second kernel,
+ * run by teams of four lanes per solve at nstr = 8 and 16), 0 = one fused kernel (or the warp-per-solve form for the
+ * smallest batches), -1 = the default: split from nstr = 16 up, and at nstr = 8 for batches between the warp-per-solve
+ * form's range and 8192 solves.  No effect at other stream counts. */
 int b200disort_set_layer_split(b200disort_handle* h, int mode);
 
 /* Synchronise and count non-zero status words of a device status array. */

@@ -214,7 +214,8 @@ class Disort:
         return self
 
     def set_layer_split(self, mode):
-        """nstr >= 12: 1 = layer-split form of the flux solve, 0 = the fused kernel, -1 = default for the stream count."""
+        """nstr = 4, 8, >= 12: 1 = layer-split form of the flux solve, 0 = never, -1 = default (from nstr = 16 up, and at nstr = 8
+        for batches of 1185..8192 solves); include/b200disort.h."""
         rc = self._lib.b200disort_set_layer_split(self._h, int(mode))
         if rc != _cabi.OK:
             raise RuntimeError(_cabi.strerror(rc))
