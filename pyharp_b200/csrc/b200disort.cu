@@ -339,6 +339,10 @@ int b200::launch_flux(b200disort_handle* h, SolveParams& p, cudaStream_t stream,
     if (use) {
       long chunk = env_chunk > 0 ? env_chunk : (long)h->sm_count * 256 * 2;
       chunk = std::min<long>(chunk, p.nlocal);
+      // (the scratch is nlyr x ~(nn^2 + nn) x 16 bytes per solve of the chunk: 82 KB at nstr = 16, 60 layers.  Many-layer
+      // columns halve the chunk down to half a resident wave rather than take more than 8 GB)
+      if (env_chunk <= 0)
+        while (inst->split_scratch(p.nlyr, chunk) > ((size_t)8 << 30) && chunk > (long)h->sm_count * 128) chunk = (chunk + 1) / 2;
       const size_t need = inst->split_scratch(p.nlyr, chunk);
       int rc = ensure_dev(ws, ws_bytes, need);
       if (rc != B200DISORT_OK) return rc;

@@ -200,3 +200,36 @@ def test_layer_split_matches_fused_kernel(cuda_device, nstr):
     assert float(np.max(np.abs(res[0] - res[1]) / scale)) < 1e-12
     assert (res[0][:, ::7, 0, 1] == 0).any()       # some columns are cut off before the surface
     assert _relerr(res[1], _oracle(wl)) < RTOL
+
+
+def test_layer_split_random_batch_thermal_and_beam(cuda_device):
+    """nstr = 16, 3 x 1500 solves with beam AND thermal sources, random optical depths over five decades: the team adding
+    kernel (groups of 8 solves per warp, the last group partly filled) against the fused kernel, and a sample against the
+    oracle."""
+    nstr, nw, nc, nl = 16, 3, 1500 + 3, 17
+    rng = np.random.default_rng(2026)
+    prop = np.zeros((nw, nc, nl, 2 + nstr))
+    prop[..., 0] = 10.0 ** rng.uniform(-4, 1.0, (nw, nc, nl))
+    prop[..., 1] = rng.uniform(0.0, 0.9999, (nw, nc, nl))
+    g = rng.uniform(0.0, 0.9, (nw, nc, nl))
+    for k in range(nstr):
+        prop[..., 2 + k] = g ** (k + 1)
+    bc = {"fbeam": rng.uniform(0.5, 4, (nw, nc)), "umu0": rng.uniform(0.1, 0.99, (nw, nc)), "albedo": rng.uniform(0, 1, (nw, nc)),
+          "btemp": np.full((nw, nc), 290.0), "ttemp": np.full((nw, nc), 100.0), "temis": np.full((nw, nc), 0.5)}
+    x, _ = np.polynomial.legendre.leggauss(nstr // 2)
+    for q in 0.5 * (x + 1):
+        bc["umu0"] = np.where(np.abs(bc["umu0"] - q) / bc["umu0"] < 1e-3, bc["umu0"] * 1.01, bc["umu0"])
+    temf = np.linspace(280.0, 190.0, nl + 1)[None, :].repeat(nc, 0) + rng.uniform(-5, 5, (nc, 1))
+    wl = W.Workload("split_rand", nstr, "lamber,quiet,onlyfl,planck", prop, bc, temf, np.array([200.0, 700.0, 1400.0]),
+                    np.array([700.0, 1400.0, 1420.0]))
+    t = lambda a: torch.from_numpy(a).to(cuda_device)
+    res = []
+    for split in (0, 1):
+        ds = Disort(wl.options()).set_layer_split(split)
+        res.append(ds.forward(t(prop), {k: t(v) for k, v in bc.items()}, t(temf)).cpu().numpy())
+        assert int(ds.status().abs().sum()) == 0
+    scale = np.max(np.abs(res[0]), axis=(2, 3), keepdims=True)
+    assert float(np.max(np.abs(res[0] - res[1]) / scale)) < 1e-11
+    sub = W.Workload("split_rand_sub", nstr, wl.flag_tokens, prop[:, :40], {k: v[:, :40] for k, v in bc.items()}, temf[:40],
+                     wl.wave_lower, wl.wave_upper)
+    assert _relerr(res[1][:, :40], _oracle(sub)) < RTOL
