@@ -181,8 +181,12 @@ def test_radiation_band_guarded_mixing(cuda_device):
 
 @pytest.mark.parametrize("name,kw", [("amars_lw", dict(nwave=32, ncol=70, nlyr=30)), ("lbl", dict(nwave=700, ncol=1, nlyr=20)),
                                      ("lbl", dict(nwave=300, ncol=8, nlyr=20)), ("gcm", dict(nwave=4, ncol=40, nlyr=12)),
-                                     ("amars_sw", dict(nwave=40, ncol=3, nlyr=20))],
-                         ids=["lw_nstr8", "lbl_nstr4_one_column", "lbl_nstr4_eight_columns", "gcm_nstr16", "sw_three_columns"])
+                                     ("amars_sw", dict(nwave=40, ncol=3, nlyr=20)),
+                                     # batches in the layer-split form's range at nstr = 8 (team adding kernel): one column =
+                                     # replicated band-flux buffer, 40 columns = plain reductions
+                                     ("amars_sw", dict(nwave=3001, ncol=1, nlyr=20)), ("amars_lw", dict(nwave=64, ncol=40, nlyr=24))],
+                         ids=["lw_nstr8", "lbl_nstr4_one_column", "lbl_nstr4_eight_columns", "gcm_nstr16", "sw_three_columns",
+                              "sw_split_team_one_column", "lw_split_team_forty_columns"])
 def test_solve_band_entry(cuda_device, name, kw):
     """b200disort_solve_band: solve + fused band integration == reduce_band(forward()) (the two-pass form)."""
     wl = W.make(name, **kw)
