@@ -601,10 +601,14 @@ B200_HD void solve_flux_layerwise(const SolveParams& p, const QT& qt, long s, do
 }
 
 // Layer-split form (flux_inst.cu, nstr >= 12): the phases of a solve as separate kernels -- unrolled or rolled bodies
-// as for solve_flux_one
+// as for solve_flux_one, with their own limit (the split kernels are smaller than the fused one: unrolling them at a
+// stream count whose fused kernel stays rolled costs less compile time)
+#ifndef B200_SPLIT_UNROLL_MAX_NN
+#define B200_SPLIT_UNROLL_MAX_NN B200_UNROLL_MAX_NN
+#endif
 template <int NN, typename QT>
 B200_HD void solve_common_any(const SolveParams& p, const QT& qt, long s, SolveCommon<NN>& c, bool bc_planck, bool legendre) {
-  if constexpr (NN <= B200_UNROLL_MAX_NN) solve_common_u<NN>(p, qt, s, c, bc_planck, legendre);
+  if constexpr (NN <= B200_SPLIT_UNROLL_MAX_NN) solve_common_u<NN>(p, qt, s, c, bc_planck, legendre);
   else solve_common_r<NN>(p, qt, s, c, bc_planck, legendre);
 }
 template <int NN, bool NOMOM>
@@ -614,13 +618,13 @@ B200_HD void layer_depths_any(const SolveParams& p, const double* pr, int lc, do
 template <int NN, bool NOMOM, typename QT>
 B200_HD int layer_ops_any(const SolveParams& p, const QT& qt, const SolveCommon<NN>& cm, const double* pr, int lc, double taup,
                           double* ops, long ostr, const double* y0p, long y0s) {
-  if constexpr (NN <= B200_UNROLL_MAX_NN) return layer_ops_u<NN, NOMOM>(p, qt, cm, pr, lc, taup, ops, ostr, y0p, y0s);
+  if constexpr (NN <= B200_SPLIT_UNROLL_MAX_NN) return layer_ops_u<NN, NOMOM>(p, qt, cm, pr, lc, taup, ops, ostr, y0p, y0s);
   else return layer_ops_r<NN, NOMOM>(p, qt, cm, pr, lc, taup, ops, ostr, y0p, y0s);
 }
 template <int NN, int BAND, typename QT>
 B200_HD void adding_sweep_any(const SolveParams& p, const QT& qt, const SolveCommon<NN>& cm, long s, const double* pr, int ncut,
                               bool lyrcut, int st, const double* opsbuf, double* recbuf, long bstr, long blane, bool active) {
-  if constexpr (NN <= B200_UNROLL_MAX_NN) adding_sweep_u<NN, BAND>(p, qt, cm, s, pr, ncut, lyrcut, st, opsbuf, recbuf, bstr, blane, active);
+  if constexpr (NN <= B200_SPLIT_UNROLL_MAX_NN) adding_sweep_u<NN, BAND>(p, qt, cm, s, pr, ncut, lyrcut, st, opsbuf, recbuf, bstr, blane, active);
   else adding_sweep_r<NN, BAND>(p, qt, cm, s, pr, ncut, lyrcut, st, opsbuf, recbuf, bstr, blane, active);
 }
 
